@@ -1,0 +1,37 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(GOLDEN)
+
+
+def golden_sites(g, prefix):
+    sites, i = [], 0
+    while f"{prefix}_site_{i}" in g:
+        sites.append(g[f"{prefix}_site_{i}"])
+        i += 1
+    return sites
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import orthogonal_classifiers_b200 as oc
+    return oc
