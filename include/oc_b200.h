@@ -1,0 +1,157 @@
+/*
+ * oc_b200.h — C ABI of the B200-native encode + classify path of
+ * Lewis1304/Orthogonal_Classifiers.
+ *
+ * The reference has no FFI: its hot path is plain Python.
+ * Each entry point below names the reference code it replaces
+ * (paths under /root/reference).  All `*_dev` pointers are CUDA device
+ * pointers owned by the caller; every call is stream-ordered on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream) and performs no
+ * hidden synchronisation unless stated.  No torch types appear here.
+ *
+ * Return value: 0 = OK, non-zero = error (OC_E_*); the message is available
+ * from oc_last_error() (thread-local).
+ *
+ * Array layouts (identical to the reference's):
+ *   image        flat row-major 28x28 -> (n_pix,), tail zero-padded to 2^L
+ *                inside the kernel (tools.py:218-220); site n <-> bit (L-1-n)
+ *                of the flat index.
+ *   MPS site n   (d=2, a_n, a_{n+1}) row-major, a_n = min(2^n, 2^(L-n), D)
+ *                (fixed shape; rank-deficient trailing columns are zero, where
+ *                xmps' minD would trim them).  Per image the L sites are
+ *                concatenated: oc_mps_layout() gives bonds and offsets.
+ *   classifier   site n (d=2, s_n, B_n, B_{n+1}) row-major (fMPO.py:21-51,
+ *                tools.py:244-254), sites concatenated; exactly one site has
+ *                s_n > 1 (the label leg, 16 for ten classes).
+ */
+#ifndef OC_B200_H
+#define OC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OC_F32 0
+#define OC_F64 1
+#define OC_U8 2 /* input images only: value/255 is applied in-kernel */
+
+#define OC_OK 0
+#define OC_E_ARG 1      /* bad shape / unsupported size */
+#define OC_E_IMAG 2     /* classifier has a non-zero imaginary part */
+#define OC_E_CUDA 3     /* CUDA runtime error (message has the cudaError) */
+#define OC_E_CAPACITY 4 /* output buffer too small */
+
+/* encoder variants: which sweep applies the D truncation */
+#define OC_TRUNC_INLINE 0 /* truncate inside the left-to-right SVD chain */
+
+#define OC_MAX_L 10      /* n_pix <= 1024 */
+#define OC_MAX_SITES 64  /* overlap kernel: chain length (MPS stacking) */
+#define OC_MAX_LABEL 32  /* label-leg size */
+
+int oc_version(void);
+const char* oc_last_error(void);
+
+/* Test/diagnostic switches.  "force_generic" = 1 routes every call through the
+ * runtime-shaped kernels instead of the specialised ones (both are CUDA). */
+int oc_set_option(const char* key, int value);
+
+/* Shape helper for the fixed-shape MPS batch.
+ * bonds[L+1]: a_n;  site_offsets[L+1]: element offset of site n inside one
+ * image's block, site_offsets[L] = elements per image (2728 for L=10, D=32).
+ * D <= 0 means "no truncation" (the reference's D=None). */
+int oc_mps_layout(int L, int D, int32_t* bonds, int64_t* site_offsets);
+
+/* Width of one bond's row in svals_out: max_n min(2 a_n, 2^(L-n-1)). */
+int oc_svals_width(int L, int D);
+
+/* Replaces variational_mpo_classifiers.py:102-104 `mps_encoding` =
+ * [fMPS_to_QTN(image_to_mps(img, D))] (tools.py:217-234): for each of N
+ * images, pad to 2^L, run the successive truncated-SVD chain (xmps
+ * left_from_state / left_canonicalise, call site tools.py:221) and write the
+ * unit-norm left-canonical MPS.
+ *   images_dev   N rows of n_pix values, row stride `ld` elements, in_dtype
+ *                OC_F32 | OC_F64 | OC_U8
+ *   dtype        arithmetic + output type, OC_F32 | OC_F64
+ *   mps_out_dev  N * site_offsets[L] elements of `dtype`
+ *   svals_out_dev  nullable; N * L * oc_svals_width() elements: the singular
+ *                values found at step n (bond n+1), descending, zero padded
+ *   sweeps_out_dev nullable; N * L int32 Jacobi sweep counts (diagnostics)
+ * An all-zero image yields an all-zero MPS (the reference would fail). */
+int oc_encode_batch(const void* images_dev, int in_dtype, int64_t N, int n_pix,
+                    int64_t ld, int L, int D, int dtype, int trunc_mode,
+                    void* mps_out_dev, void* svals_out_dev,
+                    int32_t* sweeps_out_dev, void* stream);
+
+/* Replaces the inline expression
+ *   np.abs((mps_image.H.squeeze() @ classifier.squeeze()).data)
+ * (experiments.py:278,332-337,390-391,439-440,633,769) and, restricted to
+ * entries 0..n_labels-1, variational_mpo_classifiers.py:309-318
+ * `classifier_predictions`; argmax_out is the top-1 of
+ * `evaluate_classifier_top_k_accuracy` (:340-345).
+ *   mps_dev       N image blocks laid out as oc_mps_layout (or any bonds:
+ *                 mps_bonds_host[L+1], sites (2, a_n, a_{n+1}) concatenated)
+ *   clf_dev       packed classifier (oc_pack_classifier layout) of `dtype`
+ *   clf_bonds_host[L+1], clf_s_host[L]   host int arrays
+ *   overlaps_out_dev  N * S elements (S = the label-leg size), |overlap|
+ *   argmax_out_dev    nullable; N int32, first index of the maximum */
+int oc_overlap_batch(const void* mps_dev, const int32_t* mps_bonds_host,
+                     const void* clf_dev, const int32_t* clf_bonds_host,
+                     const int32_t* clf_s_host, int L, int64_t N, int dtype,
+                     void* overlaps_out_dev, int32_t* argmax_out_dev,
+                     void* stream);
+
+/* encode + classify for one batch without the caller handling the MPS:
+ * `workspace_dev` must hold N * site_offsets[L] elements of `dtype`
+ * (pass NULL to let the library keep a grow-only internal workspace). */
+int oc_encode_classify(const void* images_dev, int in_dtype, int64_t N,
+                       int n_pix, int64_t ld, int L, int D, int dtype,
+                       int trunc_mode, const void* clf_dev,
+                       const int32_t* clf_bonds_host, const int32_t* clf_s_host,
+                       void* workspace_dev, void* overlaps_out_dev,
+                       int32_t* argmax_out_dev, void* stream);
+
+/* The integer part of variational_mpo_classifiers.py:340-345 (k = 1):
+ * out2_dev[0] += #(argmax == label), out2_dev[1] += N.  The caller zeroes
+ * out2_dev; across ranks the two int64 are summed with one NCCL all-reduce. */
+int oc_count_correct(const int32_t* argmax_dev, const uint8_t* labels_dev,
+                     int64_t N, int64_t* out2_dev, void* stream);
+
+/* Host-side, one-off: pack the reference's classifier container
+ * (fMPO(data).data / [t.data for t in qtn.tensors], tools.py:244-254; the
+ * per-site arrays load_qtn_classifier reads, tools.py:269-291) into one
+ * contiguous buffer of `dtype`.
+ *   site_ptrs_host[L]  host pointers to C-contiguous (2, s, Bl, Br) arrays of
+ *                      float64 (is_complex = 0) or complex128 (is_complex = 1)
+ *   shapes_host[4*L]   d, s, Bl, Br per site
+ * Takes the real part after checking max|imag| == 0 (fMPO.add allocates
+ * complex zeros, fMPO.py:668-679) -> OC_E_IMAG otherwise.
+ *   packed_out_host    capacity elements of `dtype`; n_written = elements used
+ *   bonds_out[L+1], s_out[L]  filled for oc_overlap_batch */
+int oc_pack_classifier(const void* const* site_ptrs_host,
+                       const int32_t* shapes_host, int L, int is_complex,
+                       int dtype, void* packed_out_host, int64_t capacity,
+                       int64_t* n_written, int32_t* bonds_out, int32_t* s_out);
+
+/* End-to-end convenience with HOST buffers (what a reference user holds):
+ * copies the images to the device, encodes, classifies, copies |overlaps| and
+ * argmax back, synchronises `stream`.  Device scratch is kept grow-only inside
+ * the library.  images_host may be pageable or pinned. */
+int oc_classify_host(const void* images_host, int in_dtype, int64_t N,
+                     int n_pix, int64_t ld, int L, int D, int dtype,
+                     int trunc_mode, const void* clf_packed_host,
+                     int64_t clf_elems, const int32_t* clf_bonds_host,
+                     const int32_t* clf_s_host, void* overlaps_out_host,
+                     int32_t* argmax_out_host, void* stream);
+
+/* Diagnostics: peak-FMA microbenchmark kernel used by bench.py to measure the
+ * fp32 FMA roofline denominator on the device it runs on.  Launches one
+ * kernel of `iters` dependent-free FMA chains; returns flops executed. */
+int oc_fma_peak_launch(int64_t iters, float* sink_dev, double* flops_out,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OC_B200_H */

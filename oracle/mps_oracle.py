@@ -168,14 +168,9 @@ def bond_singular_values(f_image: np.ndarray) -> list[np.ndarray]:
 # overlap  (experiments.py:332-337)
 # --------------------------------------------------------------------------
 
-def overlaps_chain(mps_sites, clf_sites) -> np.ndarray:
-    """|<image| classifier>| with every label leg left open.
-
-    mps_sites: L arrays (2, a_n, a_{n+1}); clf_sites: L arrays
-    (2, s_n, B_n, B_{n+1}) (fMPO.py:21-51 / tools.py:244-254 layout).
-    Returns the abs of the contraction over physical legs and bonds, shape
-    (prod s_n,) — (16,) for a one-hairy-site classifier.  quimb's ``.H`` is a
-    complex conjugate of the image (real here)."""
+def _overlaps_open_legs(mps_sites, clf_sites) -> np.ndarray:
+    """Left-to-right contraction carrying every open label leg (any number of
+    hairy sites; slow)."""
     env = np.ones((1, 1, 1), dtype=np.result_type(*[w.dtype for w in clf_sites], np.float64))
     for A, W in zip(mps_sites, clf_sites):
         # env[a, B, S] * conj(A)[d, a, a'] * W[d, s, B, B'] -> env'[a', B', S*s]
@@ -183,6 +178,37 @@ def overlaps_chain(mps_sites, clf_sites) -> np.ndarray:
         t = np.einsum("dxBS,dsBY->xYSs", t, W)
         env = t.reshape(t.shape[0], t.shape[1], -1)
     return np.abs(env.reshape(-1))
+
+
+def overlaps_chain(mps_sites, clf_sites) -> np.ndarray:
+    """|<image| classifier>| with every label leg left open.
+
+    mps_sites: L arrays (2, a_n, a_{n+1}); clf_sites: L arrays
+    (2, s_n, B_n, B_{n+1}) (fMPO.py:21-51 / tools.py:244-254 layout).
+    Returns the abs of the contraction over physical legs and bonds, shape
+    (prod s_n,) — (16,) for a one-hairy-site classifier.  quimb's ``.H`` is a
+    complex conjugate of the image (real here).  For one hairy site the
+    contraction order is the one an optimal path search finds: left
+    environment, right environment, centre (matmul-shaped steps)."""
+    hairy = [n for n, W in enumerate(clf_sites) if W.shape[1] > 1]
+    if len(hairy) > 1:
+        return _overlaps_open_legs(mps_sites, clf_sites)
+    L = len(clf_sites)
+    c = hairy[0] if hairy else L - 1
+    EL = np.ones((1, 1))
+    for n in range(c):                      # EL[a, B]
+        A, W = np.conj(mps_sites[n]), clf_sites[n][:, 0]
+        EL = sum(A[d].T @ (EL @ W[d]) for d in range(2))
+    ER = np.ones((1, 1))
+    for n in range(L - 1, c, -1):           # ER[a, B]
+        A, W = np.conj(mps_sites[n]), clf_sites[n][:, 0]
+        ER = sum((A[d] @ ER) @ W[d].T for d in range(2))
+    A, W = np.conj(mps_sites[c]), clf_sites[c]
+    out = 0
+    for d in range(2):
+        H = (EL.T @ A[d]) @ ER              # (B, B')
+        out = out + np.tensordot(W[d], H, axes=([1, 2], [0, 1]))
+    return np.abs(np.atleast_1d(out))
 
 
 def dense_classifier(clf_sites) -> np.ndarray:

@@ -1,0 +1,293 @@
+"""Batched host API over the C ABI: whole data sets per call instead of the
+reference's one-image-per-Python-iteration loops
+(/root/reference/variational_mpo_classifiers.py:102-104, experiments.py:332-337).
+
+torch is used only for device memory and streams; all arithmetic happens in the
+CUDA library (``_lib``).  Nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import OC_F32, OC_F64, OC_U8, check, i32_array, lib
+
+_TORCH_DT = {"f32": torch.float32, "f64": torch.float64}
+_OC_DT = {"f32": OC_F32, "f64": OC_F64}
+_NP_DT = {"f32": np.float32, "f64": np.float64}
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("orthogonal_classifiers_b200 needs a CUDA device; there is no CPU path")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream_ptr() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def set_force_generic(flag: bool) -> None:
+    """Route calls through the runtime-shaped CUDA kernels (test aid)."""
+    check(lib.oc_set_option(b"force_generic", int(bool(flag))))
+
+
+def n_sites_for(n_pix: int) -> int:
+    """tools.py:218 — L = ceil(log2(n_pix))."""
+    return max(1, int(np.ceil(np.log2(n_pix))))
+
+
+def mps_layout(L: int, D: int | None):
+    bonds = (C.c_int32 * (L + 1))()
+    offs = (C.c_int64 * (L + 1))()
+    check(lib.oc_mps_layout(L, 0 if D is None else int(D), bonds, offs))
+    return list(bonds), list(offs)
+
+
+def _in_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return OC_F32
+    if t.dtype == torch.float64:
+        return OC_F64
+    if t.dtype == torch.uint8:
+        return OC_U8
+    raise TypeError(f"unsupported image dtype {t.dtype}")
+
+
+def to_device_images(images, device=None) -> torch.Tensor:
+    """(N, n_pix) float32/float64/uint8, numpy or torch, -> device tensor with
+    unit inner stride.  float64 host arrays are converted to float32 on the
+    host only when the compute dtype is f32 (done by the caller)."""
+    dev = _device(device)
+    if isinstance(images, torch.Tensor):
+        t = images
+    else:
+        arr = np.asarray(images)
+        if arr.ndim == 1:
+            arr = arr[None]
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+    if t.ndim != 2:
+        raise ValueError("images must be (N, n_pix)")
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+@dataclass
+class MPSBatch:
+    """N image MPSs in the fixed-shape layout of include/oc_b200.h.
+
+    ``data`` is a device tensor (N, elems_per_image); site n of image i is
+    ``data[i, offsets[n]:offsets[n+1]].view(2, bonds[n], bonds[n+1])`` — the
+    reference's site layout (d, Dl, Dr) (tools.py:224-234)."""
+    data: torch.Tensor
+    bonds: list
+    offsets: list
+    L: int
+    D: int | None
+    dtype: str
+    svals: torch.Tensor | None = None   # (N, L, width)
+    sweeps: torch.Tensor | None = None  # (N, L) int32
+
+    def __len__(self) -> int:
+        return self.data.shape[0]
+
+    def site(self, i: int, n: int) -> torch.Tensor:
+        return self.data[i, self.offsets[n]:self.offsets[n + 1]].view(2, self.bonds[n], self.bonds[n + 1])
+
+    def sites_numpy(self, i: int, trim: bool = False) -> list:
+        """Site arrays of image i on the host.  ``trim`` removes the zero
+        trailing bond columns/rows (what xmps' minD does)."""
+        row = self.data[i].cpu().numpy()
+        out = [row[self.offsets[n]:self.offsets[n + 1]].reshape(2, self.bonds[n], self.bonds[n + 1])
+               for n in range(self.L)]
+        if trim:
+            keep = [1]
+            for n in range(self.L - 1):
+                nz = np.nonzero(np.any(out[n] != 0, axis=(0, 1)))[0]
+                keep.append(int(nz.max()) + 1 if nz.size else 1)
+            keep.append(1)
+            out = [a[:, :keep[n], :keep[n + 1]] for n, a in enumerate(out)]
+        return out
+
+
+def encode_images(images, D: int | None, dtype: str = "f32", return_svals: bool = False,
+                  return_sweeps: bool = False, device=None) -> MPSBatch:
+    """Batched ``mps_encoding`` (variational_mpo_classifiers.py:102-104):
+    every image -> unit-norm left-canonical MPS truncated to bond D."""
+    t = to_device_images(images, device)
+    N, n_pix = t.shape
+    L = n_sites_for(n_pix)
+    bonds, offs = mps_layout(L, D)
+    dev = t.device
+    out = torch.empty((N, offs[L]), dtype=_TORCH_DT[dtype], device=dev)
+    svals = sweeps = None
+    if return_svals:
+        w = lib.oc_svals_width(L, 0 if D is None else int(D))
+        svals = torch.zeros((N, L, w), dtype=_TORCH_DT[dtype], device=dev)
+    if return_sweeps:
+        sweeps = torch.zeros((N, L), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.oc_encode_batch(
+            t.data_ptr(), _in_dtype(t), N, n_pix, t.stride(0), L, 0 if D is None else int(D),
+            _OC_DT[dtype], _lib.OC_TRUNC_INLINE, out.data_ptr(),
+            svals.data_ptr() if svals is not None else None,
+            sweeps.data_ptr() if sweeps is not None else None, _stream_ptr()))
+    return MPSBatch(out, bonds, offs, L, D, dtype, svals, sweeps)
+
+
+class DeviceClassifier:
+    """A one-hairy-site classifier MPO packed on the device.
+
+    ``sites``: the reference's container — ``fMPO(...).data`` /
+    ``[t.data for t in qtn.tensors]``: L arrays (2, s_n, B_n, B_{n+1})
+    (fMPO.py:21-51, tools.py:244-254), float64 or complex128 with zero
+    imaginary part (fMPO.add, fMPO.py:668-679).  Squeezed arrays as
+    ``load_qtn_classifier`` re-expands them (tools.py:269-291) are accepted
+    in 4-d form only."""
+
+    def __init__(self, sites, dtype: str = "f32", device=None):
+        sites = [np.asarray(getattr(w, "data", w)) for w in sites]
+        L = len(sites)
+        for n, w in enumerate(sites):
+            if w.ndim != 4:
+                raise ValueError(f"classifier site {n} must be 4-d (d, s, Bl, Br), got {w.shape}")
+        is_complex = any(np.iscomplexobj(w) for w in sites)
+        host_dt = np.complex128 if is_complex else np.float64
+        sites = [np.ascontiguousarray(w, dtype=host_dt) for w in sites]
+        ptrs = (C.c_void_p * L)(*[w.ctypes.data for w in sites])
+        shapes = i32_array([d for w in sites for d in w.shape])
+        n_written = C.c_int64(0)
+        bonds = (C.c_int32 * (L + 1))()
+        s = (C.c_int32 * L)()
+        check(lib.oc_pack_classifier(ptrs, shapes, L, int(is_complex), _OC_DT[dtype], None, 0,
+                                     C.byref(n_written), bonds, s))
+        packed = np.empty(n_written.value, dtype=_NP_DT[dtype])
+        check(lib.oc_pack_classifier(ptrs, shapes, L, int(is_complex), _OC_DT[dtype],
+                                     packed.ctypes.data, packed.size, C.byref(n_written), bonds, s))
+        self.L = L
+        self.dtype = dtype
+        self.bonds = list(bonds)
+        self.s = list(s)
+        self.S = max(self.s)
+        self.centre = int(np.argmax(self.s)) if self.S > 1 else L - 1
+        self.packed_host = packed
+        self._bonds_c = bonds
+        self._s_c = s
+        self.device = _device(device)
+        self.packed = torch.from_numpy(packed).to(self.device)
+
+    def to(self, device) -> "DeviceClassifier":
+        self.device = _device(device)
+        self.packed = self.packed.to(self.device)
+        return self
+
+
+def _as_classifier(classifier, dtype: str, device=None) -> DeviceClassifier:
+    if isinstance(classifier, DeviceClassifier):
+        if classifier.dtype != dtype:
+            raise ValueError(f"classifier packed as {classifier.dtype}, requested {dtype}")
+        return classifier
+    sites = getattr(classifier, "tensors", None)
+    if sites is None:
+        sites = getattr(classifier, "data", classifier)
+    return DeviceClassifier(sites, dtype=dtype, device=device)
+
+
+def overlaps_from_mps(mps: MPSBatch, classifier, return_argmax: bool = True):
+    """Device tensors (N, S) |overlap| and (N,) int32 argmax."""
+    clf = _as_classifier(classifier, mps.dtype, mps.data.device)
+    if clf.L != mps.L:
+        raise ValueError(f"classifier has {clf.L} sites, images have {mps.L}")
+    N = len(mps)
+    dev = mps.data.device
+    ov = torch.empty((N, clf.S), dtype=_TORCH_DT[mps.dtype], device=dev)
+    am = torch.empty((N,), dtype=torch.int32, device=dev) if return_argmax else None
+    with torch.cuda.device(dev):
+        check(lib.oc_overlap_batch(
+            mps.data.data_ptr(), i32_array(mps.bonds), clf.packed.data_ptr(), clf._bonds_c, clf._s_c,
+            mps.L, N, _OC_DT[mps.dtype], ov.data_ptr(), am.data_ptr() if am is not None else None,
+            _stream_ptr()))
+    return ov, am
+
+
+def classify_device(images_dev: torch.Tensor, clf: DeviceClassifier, D: int | None,
+                    workspace: torch.Tensor | None = None, out=None):
+    """encode + classify with device-resident inputs; returns device tensors
+    (overlaps (N, S), argmax (N,)).  ``workspace``: optional (N, elems) MPS
+    scratch to avoid the library's internal allocation."""
+    N, n_pix = images_dev.shape
+    L = n_sites_for(n_pix)
+    dev = images_dev.device
+    if out is None:
+        ov = torch.empty((N, clf.S), dtype=_TORCH_DT[clf.dtype], device=dev)
+        am = torch.empty((N,), dtype=torch.int32, device=dev)
+    else:
+        ov, am = out
+    with torch.cuda.device(dev):
+        check(lib.oc_encode_classify(
+            images_dev.data_ptr(), _in_dtype(images_dev), N, n_pix, images_dev.stride(0), L,
+            0 if D is None else int(D), _OC_DT[clf.dtype], _lib.OC_TRUNC_INLINE,
+            clf.packed.data_ptr(), clf._bonds_c, clf._s_c,
+            workspace.data_ptr() if workspace is not None else None,
+            ov.data_ptr(), am.data_ptr(), _stream_ptr()))
+    return ov, am
+
+
+def label_overlaps(images_or_mps, classifier, D_encode: int | None = 32, dtype: str = "f32",
+                   device=None) -> np.ndarray:
+    """The reference's inline prediction expression, batched:
+    ``[np.abs((mps.H.squeeze() @ classifier.squeeze()).data) for mps in ...]``
+    (experiments.py:332-337) -> (N, 16) float64 host array."""
+    if isinstance(images_or_mps, MPSBatch):
+        ov, _ = overlaps_from_mps(images_or_mps, classifier, return_argmax=False)
+    elif hasattr(images_or_mps, "batch") and isinstance(images_or_mps.batch, MPSBatch):
+        ov, _ = overlaps_from_mps(images_or_mps.batch, classifier, return_argmax=False)
+    else:
+        t = to_device_images(images_or_mps, device)
+        clf = _as_classifier(classifier, dtype, t.device)
+        ov, _ = classify_device(t, clf, D_encode)
+    return ov.double().cpu().numpy()
+
+
+def classify(images, classifier, D_encode: int | None = 32, dtype: str = "f32", device=None):
+    """Host in, host out: (overlaps (N, S) float64, argmax (N,) int32)."""
+    t = to_device_images(images, device)
+    clf = _as_classifier(classifier, dtype, t.device)
+    ov, am = classify_device(t, clf, D_encode)
+    return ov.double().cpu().numpy(), am.cpu().numpy()
+
+
+def count_correct(argmax_dev: torch.Tensor, labels_dev: torch.Tensor) -> torch.Tensor:
+    """Device int64[2] = (correct, total); integer part of
+    evaluate_classifier_top_k_accuracy (k = 1)."""
+    if labels_dev.dtype != torch.uint8:
+        labels_dev = labels_dev.to(torch.uint8)
+    out = torch.zeros(2, dtype=torch.int64, device=argmax_dev.device)
+    with torch.cuda.device(argmax_dev.device):
+        check(lib.oc_count_correct(argmax_dev.data_ptr(), labels_dev.data_ptr(), argmax_dev.numel(),
+                                   out.data_ptr(), _stream_ptr()))
+    return out
+
+
+def evaluate(images, labels, classifier, D_encode: int | None = 32, dtype: str = "f32",
+             device=None, all_reduce: bool = True) -> float:
+    """Top-1 accuracy of this rank's shard, summed over ranks with one
+    all-reduce of two int64 when torch.distributed is initialised."""
+    t = to_device_images(images, device)
+    clf = _as_classifier(classifier, dtype, t.device)
+    _, am = classify_device(t, clf, D_encode)
+    lab = torch.as_tensor(np.asarray(labels), dtype=torch.uint8).to(t.device)
+    counts = count_correct(am, lab)
+    if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(counts)
+    c = counts.cpu()
+    return float(c[0].item()) / max(1, int(c[1].item()))

@@ -13,6 +13,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the .so is git-ignored: build it in-tree when missing or stale (nvcc
+    # cross-compiles sm_100a without a GPU)
+    from orthogonal_classifiers_b200.build import build_library, needs_build
+    if needs_build():
+        build_library()
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,201 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the numpy fp64
+oracle and the fixtures produced by the reference's own code.
+
+Tolerances (BASELINE.json north_star): gauge-invariant quantities within 1e-5
+(fp32, relative to sigma_max / the largest overlap) or 1e-10 (fp64); labels
+equal except declared near-ties (top-2 gap < 1e-6)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_sites
+from orthogonal_classifiers_b200.synthetic import (adversarial_images, random_classifier,
+                                                    synthetic_images)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f32": 1e-5, "f64": 1e-10}
+
+
+def _state_err(a, b):
+    return min(np.abs(a - b).max(), np.abs(a + b).max())
+
+
+def _check_encoding(oc, imgs, D, dtype, check_canonical=True):
+    batch = oc.encode_images(imgs, D, dtype=dtype, return_svals=True)
+    sv = batch.svals.cpu().numpy().astype(np.float64)
+    tol = TOL[dtype]
+    for i, im in enumerate(imgs):
+        sites = [s.astype(np.float64) for s in batch.sites_numpy(i)]
+        assert [s.shape for s in sites] == [(2, a, b) for a, b in zip(batch.bonds[:-1], batch.bonds[1:])]
+        if not im.any():
+            assert all(not s.any() for s in sites)
+            continue
+        ref_sites, ref_sv = oracle.encode_image(im, D, "inline")
+        st = oracle.mps_to_state(sites)
+        # unit norm
+        assert abs(np.linalg.norm(st) - 1) < 10 * tol
+        smax = ref_sv[0][0]
+        for n in range(batch.L):
+            m = min(sv.shape[2], len(ref_sv[n]))
+            assert np.abs(sv[i, n, :m] - ref_sv[n][:m]).max() <= tol * max(smax, ref_sv[n][0]), (i, n)
+            assert np.all(sv[i, n, m:] <= tol * smax)
+        if check_canonical:
+            for n, A in enumerate(sites):
+                d, l, r = A.shape
+                M = A.reshape(d * l, r)
+                G = M.T @ M
+                nz = np.diag(G) > 0.5
+                assert np.abs(G[np.ix_(nz, nz)] - np.eye(nz.sum())).max() < 20 * tol, (i, n)
+                assert np.abs(G[~nz]).max(initial=0) < 20 * tol
+        yield i, st, ref_sites
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_exact_encoding_reproduces_image(gpu_lib, dtype):
+    """D >= 32: the MPS is x/|x| exactly."""
+    imgs = np.concatenate([synthetic_images(48, seed=3), adversarial_images()])
+    for i, st, _ in _check_encoding(gpu_lib, imgs, 32, dtype):
+        x, _ = oracle.pad_image(imgs[i])
+        assert _state_err(st, x / np.linalg.norm(x)) < TOL[dtype], i
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+@pytest.mark.parametrize("D", [2, 4, 8, 10, 16])
+def test_truncated_encoding_matches_inline_oracle(gpu_lib, dtype, D):
+    """D < 32 (parity unpinned against xmps; pinned against the inline
+    truncated-SVD oracle).  Images whose cut falls in a near-degenerate pair
+    of singular values are declared ties and skipped."""
+    imgs = np.concatenate([synthetic_images(32, seed=4), adversarial_images()])
+    checked = 0
+    for i, st, ref_sites in _check_encoding(gpu_lib, imgs, D, dtype):
+        _, ref_sv = oracle.encode_image(imgs[i], D, "inline")
+        gaps = [(s[D - 1] - s[D]) / s[0] for s in ref_sv if len(s) > D]
+        if gaps and min(gaps) < (1e-2 if dtype == "f32" else 1e-6):
+            continue
+        ref = oracle.mps_to_state(ref_sites)
+        assert _state_err(st, ref) < (50 if dtype == "f32" else 1e4) * TOL[dtype], (i, D)
+        checked += 1
+    assert checked >= 8
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["e32_b32_f32_ortho", "e32_b32_f32_nonortho", "e32_b8_f8_ortho",
+                                  "e32_b32_f32_last_ortho", "e32_b32_f32_last_nonortho"])
+def test_predictions_match_reference_fixtures(gpu_lib, golden, dtype, name):
+    """encode + overlap vs the arrays the reference's own code produced
+    (experiments.py:332-337 through tests/golden/generate_golden.py)."""
+    clf = golden_sites(golden, f"clf_{name}")
+    ref = golden[f"pred_{name}"]
+    ov, am = gpu_lib.classify(golden["x_test"], clf, 32, dtype=dtype)
+    assert ov.shape == ref.shape == (16, 16)
+    assert np.abs(ov - ref).max() <= TOL[dtype] * ref.max()
+    srt = np.sort(ref, axis=1)
+    tie = (srt[:, -1] - srt[:, -2]) < 1e-6
+    assert np.all((am == np.argmax(ref, axis=1)) | tie)
+    # mirrored entry points give the same numbers
+    mps = gpu_lib.mps_encoding(golden["x_test"], 32, dtype=dtype)
+    p10 = np.array(gpu_lib.classifier_predictions(gpu_lib.data_to_QTN(clf), mps, 10))
+    assert p10.shape == (16, 10)
+    assert np.abs(p10 - ref[:, :10]).max() <= TOL[dtype] * ref.max()
+    if "last" not in name:
+        acc = gpu_lib.evaluate_classifier_top_k_accuracy(ov, golden["y_test"], 1)
+        assert acc == golden[f"acc_{name}"][0]
+        inline = np.abs((mps[3].H.squeeze() @ gpu_lib.data_to_QTN(clf).squeeze()).data)
+        assert np.abs(inline - ref[3]).max() <= TOL[dtype] * ref.max()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+@pytest.mark.parametrize("D_enc,D_clf,centre", [(32, 32, 5), (10, 32, 5), (4, 8, 5), (32, 36, 9), (16, 20, 9), (2, 2, 5)])
+def test_overlap_kernel_matches_chain_oracle(gpu_lib, dtype, D_enc, D_clf, centre):
+    """Overlap kernel alone: feed it the GPU's own MPS and compare with the
+    oracle contraction of the same site tensors (gauge-proof)."""
+    imgs = np.concatenate([synthetic_images(24, seed=6), adversarial_images()])
+    clf = random_classifier(10, D_clf, centre=centre, seed=D_clf)
+    batch = gpu_lib.encode_images(imgs, D_enc, dtype=dtype)
+    ov = gpu_lib.label_overlaps(batch, clf)
+    ref = np.array([oracle.overlaps_chain([s.astype(np.float64) for s in batch.sites_numpy(i)], clf)
+                    for i in range(len(imgs))])
+    assert np.abs(ov - ref).max() <= TOL[dtype] * ref.max()
+
+
+def test_small_chains_and_untruncated_vectors(gpu_lib):
+    """mps_encoding(label_vectors_16, None) (experiments.py:679,689): L = 4."""
+    rng = np.random.default_rng(0)
+    for n_pix in (2, 3, 16, 100, 512, 1000):
+        v = np.abs(rng.standard_normal((5, n_pix)))
+        for dtype in ("f32", "f64"):
+            batch = gpu_lib.encode_images(v, None, dtype=dtype)
+            for i in range(5):
+                st = oracle.mps_to_state([s.astype(np.float64) for s in batch.sites_numpy(i)])
+                x, L = oracle.pad_image(v[i])
+                assert batch.L == L
+                assert _state_err(st, x / np.linalg.norm(x)) < TOL[dtype]
+
+
+def test_empty_and_ragged_batches(gpu_lib):
+    imgs = synthetic_images(7, seed=1)
+    clf = random_classifier()
+    ov0, am0 = gpu_lib.classify(imgs[:0], clf, 32)
+    assert ov0.shape == (0, 16) and am0.shape == (0,)
+    full, _ = gpu_lib.classify(imgs, clf, 32)
+    for n in (1, 3, 5):
+        part, _ = gpu_lib.classify(imgs[:n], clf, 32)
+        np.testing.assert_array_equal(part, full[:n])     # batch-size independent, bit-exact
+    # strided rows / uint8 input
+    wide = np.zeros((7, 800), np.float32)
+    wide[:, :784] = imgs
+    import torch
+    ovw, _ = gpu_lib.classify(torch.from_numpy(wide)[:, :784], clf, 32)
+    np.testing.assert_array_equal(ovw, gpu_lib.classify(imgs.astype(np.float32), clf, 32)[0])
+    u8 = np.round(imgs * 255).astype(np.uint8)
+    ovu, _ = gpu_lib.classify(u8, clf, 32)
+    assert np.abs(ovu - full).max() < 1e-5 * full.max()
+
+
+def test_count_correct_and_evaluate(gpu_lib):
+    import torch
+    rng = np.random.default_rng(5)
+    am = rng.integers(0, 16, 100_003).astype(np.int32)
+    lab = rng.integers(0, 10, 100_003).astype(np.uint8)
+    out = gpu_lib.count_correct(torch.from_numpy(am).cuda(), torch.from_numpy(lab).cuda()).cpu().numpy()
+    assert out.tolist() == [int((am == lab).sum()), am.size]
+    imgs = synthetic_images(64, seed=2, labels=np.arange(64) % 10)
+    clf = random_classifier()
+    ov, pred = gpu_lib.classify(imgs, clf, 32)
+    acc = gpu_lib.evaluate(imgs, np.arange(64) % 10, clf, 32)
+    assert acc == np.mean(pred == np.arange(64) % 10)
+    assert acc == gpu_lib.evaluate_classifier_top_k_accuracy(ov, np.arange(64) % 10, 1)
+
+
+def test_full_split_labels_match_dense_oracle(gpu_lib, golden):
+    """10k test split at D_encode = D_total = 32: overlaps == |x_hat^T W|
+    (size-independent property); labels bit-exact except near-ties."""
+    n = 10_000
+    labels = np.arange(n) % 10
+    imgs = synthetic_images(n, seed=21, labels=labels)
+    clf = golden_sites(golden, "clf_e32_b32_f32_ortho")
+    ref = oracle.overlaps_dense(imgs, oracle.dense_classifier(clf))
+    ov, am = gpu_lib.classify(imgs.astype(np.float32), clf, 32)
+    assert np.abs(ov - ref).max() <= 1e-5 * ref.max()
+    srt = np.sort(ref, axis=1)
+    tie = (srt[:, -1] - srt[:, -2]) < 1e-6 * 10  # fp32 overlaps carry ~1e-6 abs error
+    assert np.all((am == np.argmax(ref, axis=1)) | tie)
+    assert tie.sum() < 20
+
+
+def test_self_overlap_known_answer(gpu_lib):
+    """test_variational_mpo_classifiers.py:446-457: an image against its own
+    class-encoded MPO overlaps 1.000."""
+    imgs = synthetic_images(4, seed=8)
+    bits = oracle.hairy_bitstrings(10, 10, centre=5)
+    for k, im in enumerate(imgs):
+        sites, _ = oracle.encode_image(im, 32)
+        full = [np.zeros((2, a, b)) for a, b in zip([1, 2, 4, 8, 16, 32, 16, 8, 4, 2], [2, 4, 8, 16, 32, 16, 8, 4, 2, 1])]
+        for f, s in zip(full, sites):
+            f[:, :s.shape[1], :s.shape[2]] = s
+        mpo = oracle.class_encode(full, k, bits)
+        ov, am = gpu_lib.classify(im[None], mpo, 32, dtype="f64")
+        assert abs(ov[0, k] - 1) < 1e-10 and am[0] == k
+        ov32, _ = gpu_lib.classify(im[None], mpo, 32)
+        assert np.round(ov32[0, k], 3) == 1.0
