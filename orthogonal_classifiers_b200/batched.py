@@ -76,9 +76,14 @@ def to_device_images(images, device=None) -> torch.Tensor:
         raise ValueError("images must be (N, n_pix)")
     if t.device != dev:
         t = t.to(dev, non_blocking=True)
-    if t.stride(1) != 1:
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
         t = t.contiguous()
     return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Row stride in elements (a single row may report any stride)."""
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1]
 
 
 @dataclass
@@ -137,7 +142,7 @@ def encode_images(images, D: int | None, dtype: str = "f32", return_svals: bool 
         sweeps = torch.zeros((N, L), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         check(lib.oc_encode_batch(
-            t.data_ptr(), _in_dtype(t), N, n_pix, t.stride(0), L, 0 if D is None else int(D),
+            t.data_ptr(), _in_dtype(t), N, n_pix, _ld(t), L, 0 if D is None else int(D),
             _OC_DT[dtype], _lib.OC_TRUNC_INLINE, out.data_ptr(),
             svals.data_ptr() if svals is not None else None,
             sweeps.data_ptr() if sweeps is not None else None, _stream_ptr()))
@@ -234,7 +239,7 @@ def classify_device(images_dev: torch.Tensor, clf: DeviceClassifier, D: int | No
         ov, am = out
     with torch.cuda.device(dev):
         check(lib.oc_encode_classify(
-            images_dev.data_ptr(), _in_dtype(images_dev), N, n_pix, images_dev.stride(0), L,
+            images_dev.data_ptr(), _in_dtype(images_dev), N, n_pix, _ld(images_dev), L,
             0 if D is None else int(D), _OC_DT[clf.dtype], _lib.OC_TRUNC_INLINE,
             clf.packed.data_ptr(), clf._bonds_c, clf._s_c,
             workspace.data_ptr() if workspace is not None else None,
