@@ -203,3 +203,23 @@ def test_self_overlap_known_answer(gpu_lib):
         assert abs(ov[0, k] - 1) < 1e-10 and am[0] == k
         ov32, _ = gpu_lib.classify(im[None], mpo, 32)
         assert np.round(ov32[0, k], 3) == 1.0
+
+
+def test_generic_and_specialised_kernels_agree(gpu_lib):
+    """The runtime-shaped kernels (force_generic) and the specialised ones are
+    two CUDA implementations of the same path: same gauge-invariants."""
+    imgs = np.concatenate([synthetic_images(40, seed=14), adversarial_images()]).astype(np.float32)
+    clf = random_classifier(10, 32, centre=5, seed=3)
+    for D in (32, 10, 3):
+        fast = gpu_lib.encode_images(imgs, D, return_svals=True)
+        ov_fast = gpu_lib.label_overlaps(fast, clf)
+        gpu_lib.set_force_generic(True)
+        try:
+            gen = gpu_lib.encode_images(imgs, D, return_svals=True)
+            ov_gen = gpu_lib.label_overlaps(gen, clf)
+        finally:
+            gpu_lib.set_force_generic(False)
+        sf, sg = fast.svals.cpu().numpy(), gen.svals.cpu().numpy()
+        assert np.abs(sf - sg).max() <= 1e-5 * sg.max()
+        if D == 32:
+            assert np.abs(ov_fast - ov_gen).max() <= 1e-5 * ov_gen.max()
