@@ -70,8 +70,8 @@ struct Scratch {
     return OC_OK;
   }
 };
-std::mutex g_mu;
-Scratch g_mps, g_img, g_clf, g_ov, g_am;
+std::mutex g_mu, g_ws_mu;
+Scratch g_mps, g_img, g_clf, g_ov, g_am, g_enc_ws;
 int g_force_generic = 0;
 
 template <typename K>
@@ -158,7 +158,15 @@ int oc_encode_batch(const void* images_dev, int in_dtype, int64_t N, int n_pix, 
 
   // specialised path: fp32, L = 10 (register-resident Jacobi chain)
   if (dtype == OC_F32 && !g_force_generic && oc::encode_fast_supported(P)) {
-    int rc = oc::encode_fast_launch(P, num_sms(), st);
+    // Psi ping-pong workspace of the step-major chain (grow-only, library-owned)
+    const int64_t chunk = std::min<int64_t>(N, oc::kEncodeChunk);
+    float* ws = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(g_ws_mu);
+      if (int rc = g_enc_ws.ensure((size_t)2 * chunk * oc::kWsStride * sizeof(float))) return rc;
+      ws = reinterpret_cast<float*>(g_enc_ws.p);
+    }
+    int rc = oc::encode_fast_launch(P, ws, num_sms(), st);
     if (rc == 0) return OC_OK;
     if (rc > 0) return fail(OC_E_CUDA, "encode_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   }

@@ -2,23 +2,25 @@
 // warp; the vectors being orthogonalised live in REGISTERS.
 //
 // Step n works on M_n (P = 2B rows, Q cols), B = b_n, Q = 2^(9-n).  Its NV
-// vectors (rows when P < Q, columns otherwise; length LEN) are spread over the
-// warp as "slots" of LP lanes; a slot owns the two vectors at line positions
-// (2k, 2k+1) — register sets T and S, each lane holding EL consecutive elements
-// of both (EL = 16 for the big steps, 4 for the small tail steps).
-// One-sided (Hestenes) Jacobi with the odd-even ordering:
+// vectors (rows when M_n is wide, columns otherwise; length LEN) are spread
+// over the warp as "slots" of LP lanes; a slot owns the two vectors at line
+// positions (2k, 2k+1) — register sets T and S, each lane holding EL
+// consecutive elements of both.  One-sided (Hestenes) Jacobi, odd-even ordering:
 //   round A: rotate (T_k, S_k)        — no communication
 //   round B: rotate (S_k, T_{k+1})    — T moves one slot down and back
 // every rotation also swaps the two line positions, so after NV rounds every
-// pair has met once (one sweep).  Squared norms are carried with the vectors
-// and updated by the rotation (refreshed from the data every sweep and
-// whenever an update cancels), so a round costs ONE dot product.  All
-// element-wise arithmetic is packed fma.rn.f32x2 (SASS FFMA2).
+// pair has met once (one sweep).  Squared norms travel with the vectors and are
+// updated by the rotation (refreshed from the data every sweep and whenever an
+// update cancels), so a round costs ONE dot product.  Element-wise arithmetic
+// is packed fma.rn.f32x2 (SASS FFMA2); rotation parameters are branch-free.
 //
-// ONE step body, parametrised at run time by a small per-step table, serves
-// all ten steps and every D: the hot loop is ~1 K instructions and stays in the
-// instruction cache (the first, fully unrolled version was 246 KB of SASS and
-// stalled on instruction fetch — profiles/encode_r1a.md).
+// STEP-MAJOR execution: the chain is cut into five kernels
+//   head (steps 0-2) | step 3 | step 4 | step 5 | tail (steps 6-9)
+// each launched over all images, Psi_n passing through a global workspace
+// (4 KB per image, L2-resident for the chunk sizes used).  Every warp on the
+// chip then runs the same few KB of fully static code.  The fused one-kernel
+// versions stalled on instruction fetch (profiles/encode_r1.md): 16 warps per
+// SM in 10 different steps do not fit the instruction cache.
 #pragma once
 #include "oc_generic.cuh"
 
@@ -50,11 +52,6 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-__device__ __forceinline__ float hsum2(u64 v) {
-  float lo, hi;
-  unpack2(v, lo, hi);
-  return lo + hi;
-}
 __device__ __forceinline__ u64 shfl2(u64 v, int src) {
   float lo, hi;
   unpack2(v, lo, hi);
@@ -62,65 +59,97 @@ __device__ __forceinline__ u64 shfl2(u64 v, int src) {
   hi = __shfl_sync(FULL, hi, src);
   return pack2(lo, hi);
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
-struct FastStep {
-  int logB, logQ;  // Psi_n is [B][2Q] in shared memory (padded to powers of two)
-  int row;         // 1: the vectors are the rows of M_n
-  int NV, LEN;     // number of vectors / their length
-  int logLP;       // lanes per slot
-  int M;           // active slots = NV / 2
-  int el16;        // 1: EL = 16 instance, 0: EL = 4
-  int R;           // rows of Psi_{n+1} kept in shared memory (padded)
-  int rpl;         // rows per lane of the U^T M product (32, 8, 2 or 1)
-};
-struct FastPlan {
-  FastStep st[OC_MAX_L];
+__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int clog2(int x) { return x <= 1 ? 0 : 1 + clog2(x / 2); }
+
+// static description of step n of the chain with bond cap DPAD (power of two)
+template <int DPAD, int N>
+struct Step {
+  static constexpr int B = cmin(cmin(1 << N, 1 << (10 - N)), DPAD);          // rows of Psi_n
+  static constexpr int Q = 1 << (9 - N);                                       // half its columns
+  static constexpr int R = cmin(cmin(1 << (N + 1), 1 << (9 - N)), DPAD);      // rows of Psi_{n+1}
+  static constexpr int P = 2 * B;
+  static constexpr bool ROW = P < Q;
+  static constexpr int NV = ROW ? P : Q;
+  static constexpr int LEN = ROW ? Q : P;
+  static constexpr int M = NV / 2;                                             // active slots
+  // lanes per slot: all 32 lanes when the vectors are long enough for >= 4
+  // elements per lane, else 4 elements per lane on fewer lanes
+  static constexpr int LP0 = NV >= 2 ? 64 / NV : 32;
+  static constexpr int EL = (LEN / LP0 >= 4) ? LEN / LP0 : cmin(4, LEN);
+  static constexpr int LP = LEN / EL;
+  static constexpr int LOGLP = clog2(LP);
+  static constexpr int E2 = EL / 2;
+  static constexpr int UEL = ROW ? cmax(2, NV / LP) : 2;                      // U-row elements per lane (even)
+  static constexpr int U2 = UEL / 2;
+  static_assert(NV == 1 || (M * LP <= 32 && LP * EL == LEN && EL % 2 == 0), "bad lane mapping");
+  static_assert(!ROW || UEL * LP >= NV, "U row does not fit");
 };
 
-template <int E2>
-__device__ __forceinline__ float group_dot(const u64 (&a)[E2], const u64 (&b)[E2], int LP) {
-  u64 acc = 0ull;
+template <int E2, int LOGLP>
+__device__ __forceinline__ float group_dot(const u64 (&a)[E2], const u64 (&b)[E2]) {
+  // independent partial sums keep the FFMA2 dependency chains short
+  constexpr int NA = E2 >= 4 ? 4 : E2;
+  u64 acc[NA];
 #pragma unroll
-  for (int e = 0; e < E2; ++e) acc = fma2(a[e], b[e], acc);
-  float v = hsum2(acc);
-  for (int o = 1; o < LP; o <<= 1) v += __shfl_xor_sync(FULL, v, o);
+  for (int e = 0; e < NA; ++e) acc[e] = mul2(a[e], b[e]);
+#pragma unroll
+  for (int e = NA; e < E2; ++e) acc[e % NA] = fma2(a[e], b[e], acc[e % NA]);
+  float v = 0.f;
+#pragma unroll
+  for (int e = 0; e < NA; ++e) {
+    float lo, hi;
+    unpack2(acc[e], lo, hi);
+    v += lo + hi;
+  }
+#pragma unroll
+  for (int o = 0; o < LOGLP; ++o) v += __shfl_xor_sync(FULL, v, 1 << o);
   return v;
 }
 
 // rotate (a, b) with cached squared norms (na, nb); afterwards a/na hold the
 // vector of the FIRST line position (b') and b/nb the second (a').
-template <int E2>
-__device__ __forceinline__ void rotate_pair(u64 (&a)[E2], u64 (&b)[E2], u64 (&ua)[2], u64 (&ub)[2],
-                                            float& na, float& nb, float thr2, bool idle, bool row,
-                                            int LP, bool& again) {
-  const float ab = group_dot<E2>(a, b, LP);
+template <int E2, int U2, int LOGLP, bool ROW>
+__device__ __forceinline__ void rotate_pair(u64 (&a)[E2], u64 (&b)[E2], u64 (&ua)[U2], u64 (&ub)[U2],
+                                            float& na, float& nb, float thr2, bool idle, bool& again) {
+  const float ab = group_dot<E2, LOGLP>(a, b);
   const float aa = na, bb = nb;
   const float d = aa * bb;
   const float ab2 = ab * ab;
   const bool rot = (ab2 > kTol2 * d) && (aa > thr2) && (bb > thr2) && !idle;
   again = again || (rot && ab2 > kQStop2 * d);
-  float c = 1.f, s = 0.f, t = 0.f;
-  if (rot) {
-    const float zeta = __fdividef(bb - aa, 2.f * ab);
-    t = __fdividef(1.f, fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
-    t = zeta < 0.f ? -t : t;
-    const float h = fmaf(t, t, 1.f);
-    float r = rsqrtf(h);
-    r = r * fmaf(-0.5f * h, r * r, 1.5f);  // Newton step: c^2 + s^2 = 1 to ~1 ulp
-    c = r;
-    s = r * t;
-  }
-  if (idle) {  // both vectors stay where they are (the second picks up a sign)
-    c = 0.f;
-    s = 1.f;
-  }
+  // branch-free; the MUFU approximations only influence how well this rotation
+  // orthogonalises the pair, never its orthogonality (c, s are renormalised)
+  const float two_ab = rot ? ab + ab : 1.f;
+  const float zeta = (bb - aa) * rcp_approx(two_ab);
+  float t = rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f)));
+  t = rot ? copysignf(t, zeta) : 0.f;
+  const float h = fmaf(t, t, 1.f);
+  float r = rsqrt_approx(h);
+  r = r * fmaf(-0.5f * h, r * r, 1.5f);  // Newton step: c^2 + s^2 = 1 to ~1 ulp
+  // idle: both vectors stay where they are (the second picks up a sign)
+  const float c = idle ? 0.f : r;
+  const float s = idle ? 1.f : r * t;
   // |a'|^2 = aa - t ab, |b'|^2 = bb + t ab; positions swap
-  float n_first = fmaf(t, ab, bb);
-  float n_second = fmaf(-t, ab, aa);
-  if (idle) {
-    n_first = aa;
-    n_second = bb;
-  }
+  float n_first = idle ? aa : fmaf(t, ab, bb);
+  float n_second = idle ? bb : fmaf(-t, ab, aa);
   const bool lost = rot && (n_second < kCancel * aa || n_first < kCancel * bb);
   const u64 c2 = pack2(c, c), s2 = pack2(s, s), ns2 = pack2(-s, -s);
 #pragma unroll
@@ -129,28 +158,27 @@ __device__ __forceinline__ void rotate_pair(u64 (&a)[E2], u64 (&b)[E2], u64 (&ua
     a[e] = fma2(s2, x, mul2(c2, y));
     b[e] = fma2(c2, x, mul2(ns2, y));
   }
-  if (row) {
+  if (ROW) {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
+    for (int e = 0; e < U2; ++e) {
       const u64 x = ua[e], y = ub[e];
       ua[e] = fma2(s2, x, mul2(c2, y));
       ub[e] = fma2(c2, x, mul2(ns2, y));
     }
   }
   if (__any_sync(FULL, lost)) {  // warp-uniform, rare after the first sweeps
-    n_first = group_dot<E2>(a, a, LP);
-    n_second = group_dot<E2>(b, b, LP);
+    n_first = group_dot<E2, LOGLP>(a, a);
+    n_second = group_dot<E2, LOGLP>(b, b);
   }
   na = n_first;
   nb = n_second;
 }
 
-template <int E2>
-__device__ __forceinline__ int jacobi_regs(u64 (&T)[E2], u64 (&S)[E2], u64 (&UT)[2], u64 (&US)[2],
-                                           float& nT, float& nS, float thr2, int lane, int logLP,
-                                           int M, bool row) {
-  const int LP = 1 << logLP;
-  const int slot = lane >> logLP;
+template <int E2, int U2, int LOGLP, int M, bool ROW>
+__device__ __forceinline__ int jacobi_regs(u64 (&T)[E2], u64 (&S)[E2], u64 (&UT)[U2], u64 (&US)[U2],
+                                           float& nT, float& nS, float thr2, int lane) {
+  constexpr int LP = 1 << LOGLP;
+  const int slot = lane >> LOGLP;
   const int src_dn = (lane + LP) & 31;
   const int src_up = (lane - LP) & 31;
   const bool idleB = slot >= M - 1;
@@ -158,29 +186,25 @@ __device__ __forceinline__ int jacobi_regs(u64 (&T)[E2], u64 (&S)[E2], u64 (&UT)
 #pragma unroll 1
   while (sweeps < kMaxSweeps) {
     bool again = false;
-    nT = group_dot<E2>(T, T, LP);
-    nS = group_dot<E2>(S, S, LP);
+    nT = group_dot<E2, LOGLP>(T, T);
+    nS = group_dot<E2, LOGLP>(S, S);
 #pragma unroll 1
     for (int rr = 0; rr < M; ++rr) {
-      rotate_pair<E2>(T, S, UT, US, nT, nS, thr2, false, row, LP, again);
+      rotate_pair<E2, U2, LOGLP, ROW>(T, S, UT, US, nT, nS, thr2, false, again);
       if (M > 1) {
-        u64 R[E2], UR[2];
+        u64 R[E2], UR[U2];
 #pragma unroll
         for (int e = 0; e < E2; ++e) R[e] = shfl2(T[e], src_dn);
         float nR = __shfl_sync(FULL, nT, src_dn);
-        if (row) {
-          UR[0] = shfl2(UT[0], src_dn);
-          UR[1] = shfl2(UT[1], src_dn);
-        } else {
-          UR[0] = UR[1] = 0ull;
-        }
-        rotate_pair<E2>(S, R, US, UR, nS, nR, thr2, idleB, row, LP, again);
+#pragma unroll
+        for (int e = 0; e < U2; ++e) UR[e] = ROW ? shfl2(UT[e], src_dn) : 0ull;
+        rotate_pair<E2, U2, LOGLP, ROW>(S, R, US, UR, nS, nR, thr2, idleB, again);
 #pragma unroll
         for (int e = 0; e < E2; ++e) T[e] = shfl2(R[e], src_up);
         nT = __shfl_sync(FULL, nR, src_up);
-        if (row) {
-          UT[0] = shfl2(UR[0], src_up);
-          UT[1] = shfl2(UR[1], src_up);
+        if (ROW) {
+#pragma unroll
+          for (int e = 0; e < U2; ++e) UT[e] = shfl2(UR[e], src_up);
         }
       }
     }
@@ -191,178 +215,158 @@ __device__ __forceinline__ int jacobi_regs(u64 (&T)[E2], u64 (&S)[E2], u64 (&UT)
   return sweeps;
 }
 
-// Psi_{n+1}[r][c] = sum_e U[e][r] M[e][c];  U staged as [e][R] in `U`,
-// M[e = s*B + l][c] = Pin[l][s*Q + c].  Lane owns column c and RPL rows.
-template <int RPL>
-__device__ __forceinline__ void utm_product(float* Pin, const float* U, int LEN, int logB, int logQ,
-                                            int R, int lane) {
-  const int Q = 1 << logQ, B = 1 << logB;
-  const int c = lane & (Q - 1), g = lane >> logQ;
-  const bool active = g * RPL < R;
-  float acc[RPL];
-#pragma unroll
-  for (int i = 0; i < RPL; ++i) acc[i] = 0.f;
-  if (active) {
-#pragma unroll 2
-    for (int e = 0; e < LEN; ++e) {
-      const int s = e >> logB, l = e & (B - 1);
-      const float m = Pin[l * 2 * Q + s * Q + c];
-      const float* u = U + e * R + g * RPL;
-      if (RPL >= 4) {
-#pragma unroll
-        for (int i = 0; i < RPL; i += 4) {
-          const float4 uv = *reinterpret_cast<const float4*>(u + i);
-          acc[i] = fmaf(uv.x, m, acc[i]);
-          acc[i + 1] = fmaf(uv.y, m, acc[i + 1]);
-          acc[i + 2] = fmaf(uv.z, m, acc[i + 2]);
-          acc[i + 3] = fmaf(uv.w, m, acc[i + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) acc[i] = fmaf(u[i], m, acc[i]);
-      }
-    }
-  }
-  __syncwarp();
-  if (active) {
-#pragma unroll
-    for (int i = 0; i < RPL; ++i) Pin[(g * RPL + i) * Q + c] = acc[i];
-  }
-  __syncwarp();
-}
+struct StepIO {
+  float* A;        // site tensor A_n of this image (global)
+  float* sv;       // svals row of this step (global) or nullptr
+  int32_t* sweeps; // sweeps slot or nullptr
+  int b_rt, r_rt;  // run-time bonds of the output layout (b_n(D), b_{n+1}(D))
+  int sv_width;
+};
 
-// One step of the chain (see file header).  Returns the buffer holding Psi_{n+1}.
-template <int EL>
-__device__ __forceinline__ float* run_step(const EncodeParams& P, const FastStep& st, int n,
-                                           int64_t img, float* Pin, float* Pout, float* mps, int lane) {
-  constexpr int E2 = EL / 2;
-  const int logLP = st.logLP, LP = 1 << logLP;
-  const int slot = lane >> logLP, sub = lane & (LP - 1);
-  const int B = 1 << st.logB, Q = 1 << st.logQ;
-  const int NV = st.NV, LEN = st.LEN, R = st.R;
-  const bool row = st.row != 0;
-  const bool act = slot < st.M;
-  const int b_rt = P.bonds[n], r_rt = P.bonds[n + 1];
-  float* A = mps + P.site_off[n];
-  float* sv = P.svals_out ? reinterpret_cast<float*>(P.svals_out) + ((size_t)img * P.L + n) * P.sv_width : nullptr;
+// One step.  Psi_n is in shared memory `Pin` laid out [B][2Q] (or, for N == 0,
+// the image in global memory).  Psi_{n+1} [R][Q] is left in shared memory; the
+// function returns the buffer holding it (Pin in column mode, Pout in row mode).
+template <int DPAD, int N>
+__device__ __forceinline__ float* jstep(const EncodeParams& P, int64_t img, const StepIO& io,
+                                        float* Pin, float* Pout, int lane) {
+  using C = Step<DPAD, N>;
+  constexpr int B = C::B, Q = C::Q, R = C::R, NV = C::NV, LEN = C::LEN, LP = C::LP, EL = C::EL;
+  constexpr int E2 = C::E2, U2 = C::U2, UEL = C::UEL, LOGLP = C::LOGLP, M = C::M;
+  constexpr bool ROW = C::ROW;
+  const int b_rt = io.b_rt, r_rt = io.r_rt;
+  float* A = io.A;
 
-  u64 T[E2], S[E2], UT[2], US[2];
-  const int idx0 = sub * EL;  // first element index held by this lane
-  // ---- load the two vectors of this slot ----
-  if (n == 0) {
-    // B = 1: T = pixels [0, 512), S = pixels [512, 1024)
-    const char* src = reinterpret_cast<const char*>(P.images);
-    const int esz = P.in_dtype == 0 ? 4 : (P.in_dtype == 1 ? 8 : 1);
-    const void* rowp = src + (size_t)img * P.ld * esz;
-    const bool vec = P.in_dtype == 0 && ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-#pragma unroll
-    for (int e = 0; e < EL; e += 4) {
-      float t[4], s[4];
-      const int iT = idx0 + e, iS = Q + idx0 + e;
-      if (vec && iT + 3 < P.n_pix) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) + iT));
-        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) t[j] = iT + j < P.n_pix ? load_pixel<float>(rowp, P.in_dtype, iT + j) : 0.f;
-      }
-      if (vec && iS + 3 < P.n_pix) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) + iS));
-        s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) s[j] = iS + j < P.n_pix ? load_pixel<float>(rowp, P.in_dtype, iS + j) : 0.f;
-      }
-      T[e / 2] = pack2(t[0], t[1]); T[e / 2 + 1] = pack2(t[2], t[3]);
-      S[e / 2] = pack2(s[0], s[1]); S[e / 2 + 1] = pack2(s[2], s[3]);
+  if constexpr (NV == 1) {
+    // last step: M (2B x 1) -> A = M / |M|; the 1x1 S.V is dropped (unit norm)
+    const int s = lane / B, l = lane % B;
+    const float v = lane < 2 * B ? Pin[l * 2 + s] : 0.f;
+    const float nn = warp_sum(v * v);
+    const float inv = nn > 0.f ? rsqrtf(nn) : 0.f;
+    if (lane < 2 * B && l < b_rt) A[s * b_rt + l] = v * inv;
+    if (io.sv) {
+      for (int k = lane; k < io.sv_width; k += 32) io.sv[k] = k == 0 ? sqrtf(nn) : 0.f;
     }
-  } else if (row) {
-    // vector j = 2l + s is the chunk [l][s*Q, s*Q + Q) of Psi_n; slot k = l
-    const float* pt = Pin + slot * 2 * Q + idx0;
-#pragma unroll
-    for (int e = 0; e < EL; e += 4) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f), s = t;
-      if (act && idx0 + e < LEN) {
-        t = *reinterpret_cast<const float4*>(pt + e);
-        s = *reinterpret_cast<const float4*>(pt + Q + e);
-      }
-      T[e / 2] = pack2(t.x, t.y); T[e / 2 + 1] = pack2(t.z, t.w);
-      S[e / 2] = pack2(s.x, s.y); S[e / 2 + 1] = pack2(s.z, s.w);
-    }
+    if (io.sweeps && lane == 0) *io.sweeps = 0;
+    return Pin;
   } else {
-    // vector c = column c of M_n; element e' = s*B + l lives at Psi_n[l][s*Q + c]
+    const int slot = lane >> LOGLP, sub = lane & (LP - 1);
+    const bool act = slot < M;
+    const int idx0 = sub * EL;
+    u64 T[E2], S[E2], UT[U2], US[U2];
+    // ---- load the two vectors of this slot ----
+    if constexpr (N == 0) {
+      // B = 1: T = pixels [0, 512), S = pixels [512, 1024)
+      const char* src = reinterpret_cast<const char*>(P.images);
+      const int esz = P.in_dtype == 0 ? 4 : (P.in_dtype == 1 ? 8 : 1);
+      const void* rowp = src + (size_t)img * P.ld * esz;
+      const bool vec = P.in_dtype == 0 && ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
 #pragma unroll
-    for (int e = 0; e < EL; e += 2) {
-      float2 v0 = make_float2(0.f, 0.f), v1 = v0;
-      const int i0 = idx0 + e, i1 = i0 + 1;
-      if (act && i0 < LEN) {
-        v0 = *reinterpret_cast<const float2*>(Pin + (i0 & (B - 1)) * 2 * Q + (i0 >> st.logB) * Q + 2 * slot);
-        v1 = *reinterpret_cast<const float2*>(Pin + (i1 & (B - 1)) * 2 * Q + (i1 >> st.logB) * Q + 2 * slot);
-      }
-      T[e / 2] = pack2(v0.x, v1.x);
-      S[e / 2] = pack2(v0.y, v1.y);
-    }
-  }
-  {
-    // U-row elements jj = 4 sub .. 4 sub + 3 (row mode: NV <= 16 so 4 per lane suffice)
-    const int j0 = sub * 4, pT = 2 * slot, pS = 2 * slot + 1;
-    const bool on = row && act;
-    UT[0] = pack2(on && j0 == pT ? 1.f : 0.f, on && j0 + 1 == pT ? 1.f : 0.f);
-    UT[1] = pack2(on && j0 + 2 == pT ? 1.f : 0.f, on && j0 + 3 == pT ? 1.f : 0.f);
-    US[0] = pack2(on && j0 == pS ? 1.f : 0.f, on && j0 + 1 == pS ? 1.f : 0.f);
-    US[1] = pack2(on && j0 + 2 == pS ? 1.f : 0.f, on && j0 + 3 == pS ? 1.f : 0.f);
-  }
-  // ---- Frobenius norm -> zero threshold ----
-  float nT = group_dot<E2>(T, T, LP), nS = group_dot<E2>(S, S, LP);
-  float fro = (sub == 0) ? nT + nS : 0.f;
-  fro = warp_sum(fro);
-  const float thr2 = kFloor2 * fro;
-
-  int sweeps = 0;
-  if (fro > 0.f) {
-    sweeps = jacobi_regs<E2>(T, S, UT, US, nT, nS, thr2, lane, logLP, st.M, row);
-    nT = group_dot<E2>(T, T, LP);
-    nS = group_dot<E2>(S, S, LP);
-  }
-  // ---- stable descending rank among the NV vectors ----
-  int rT = 0, rS = 0;
-  {
-    const int pT = 2 * slot, pS = 2 * slot + 1;
-#pragma unroll 2
-    for (int j = 0; j < NV; ++j) {
-      const float v = __shfl_sync(FULL, (j & 1) ? nS : nT, (j >> 1) << logLP);
-      rT += (v > nT) || (v == nT && j < pT);
-      rS += (v > nS) || (v == nS && j < pS);
-    }
-  }
-  const bool kT = act && nT > thr2 && rT < r_rt;
-  const bool kS = act && nS > thr2 && rS < r_rt;
-  if (sv) {
-    if (sub == 0 && act) {
-      if (rT < P.sv_width) sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
-      if (rS < P.sv_width) sv[rS] = nS > thr2 ? sqrtf(nS) : 0.f;
-    }
-    for (int k = NV + lane; k < P.sv_width; k += 32) sv[k] = 0.f;
-  }
-  if (P.sweeps_out && lane == 0) P.sweeps_out[(size_t)img * P.L + n] = sweeps;
-
-  if (row) {
-    // A_n[(s,l), rank] = U-row element jj = 2l + s
-    if (act) {
-      float ut[4], us[4];
-      unpack2(UT[0], ut[0], ut[1]); unpack2(UT[1], ut[2], ut[3]);
-      unpack2(US[0], us[0], us[1]); unpack2(US[1], us[2], us[3]);
+      for (int e = 0; e < EL; e += 4) {
+        float t[4], s[4];
+        const int iT = idx0 + e, iS = Q + idx0 + e;
+        if (vec && iT + 3 < P.n_pix) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) + iT));
+          t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int jj = sub * 4 + e;
-        const int l = jj >> 1, s = jj & 1;
-        if (jj < NV && l < b_rt) {
-          if (rT < r_rt) A[(s * b_rt + l) * r_rt + rT] = kT ? ut[e] : 0.f;
-          if (rS < r_rt) A[(s * b_rt + l) * r_rt + rS] = kS ? us[e] : 0.f;
+          for (int j = 0; j < 4; ++j) t[j] = iT + j < P.n_pix ? load_pixel<float>(rowp, P.in_dtype, iT + j) : 0.f;
         }
+        if (vec && iS + 3 < P.n_pix) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) + iS));
+          s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[j] = iS + j < P.n_pix ? load_pixel<float>(rowp, P.in_dtype, iS + j) : 0.f;
+        }
+        T[e / 2] = pack2(t[0], t[1]); T[e / 2 + 1] = pack2(t[2], t[3]);
+        S[e / 2] = pack2(s[0], s[1]); S[e / 2 + 1] = pack2(s[2], s[3]);
       }
-      // next Psi: row `rank` <- vector (zero when dropped)
-      if (idx0 < LEN) {
+    } else if constexpr (ROW) {
+      // vector j = 2l + s is the chunk [l][s*Q, s*Q + Q) of Psi_n; slot k = l
+      const float* pt = Pin + slot * 2 * Q + idx0;
+#pragma unroll
+      for (int e = 0; e < EL; e += 4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f), s = t;
+        if (act) {
+          t = *reinterpret_cast<const float4*>(pt + e);
+          s = *reinterpret_cast<const float4*>(pt + Q + e);
+        }
+        T[e / 2] = pack2(t.x, t.y); T[e / 2 + 1] = pack2(t.z, t.w);
+        S[e / 2] = pack2(s.x, s.y); S[e / 2 + 1] = pack2(s.z, s.w);
+      }
+    } else {
+      // vector c = column c of M_n; element e' = s*B + l lives at Psi_n[l][s*Q + c]
+#pragma unroll
+      for (int e = 0; e < EL; e += 2) {
+        float2 v0 = make_float2(0.f, 0.f), v1 = v0;
+        const int i0 = idx0 + e, i1 = i0 + 1;
+        if (act) {
+          v0 = *reinterpret_cast<const float2*>(Pin + (i0 % B) * 2 * Q + (i0 / B) * Q + 2 * slot);
+          v1 = *reinterpret_cast<const float2*>(Pin + (i1 % B) * 2 * Q + (i1 / B) * Q + 2 * slot);
+        }
+        T[e / 2] = pack2(v0.x, v1.x);
+        S[e / 2] = pack2(v0.y, v1.y);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < U2; ++e) {
+      const int j0 = sub * UEL + 2 * e, pT = 2 * slot, pS = 2 * slot + 1;
+      const bool on = ROW && act;
+      UT[e] = pack2(on && j0 == pT ? 1.f : 0.f, on && j0 + 1 == pT ? 1.f : 0.f);
+      US[e] = pack2(on && j0 == pS ? 1.f : 0.f, on && j0 + 1 == pS ? 1.f : 0.f);
+    }
+    // ---- Frobenius norm -> zero threshold ----
+    float nT = group_dot<E2, LOGLP>(T, T), nS = group_dot<E2, LOGLP>(S, S);
+    float fro = (sub == 0) ? nT + nS : 0.f;
+    fro = warp_sum(fro);
+    const float thr2 = kFloor2 * fro;
+
+    int sweeps = 0;
+    if (fro > 0.f) {
+      sweeps = jacobi_regs<E2, U2, LOGLP, M, ROW>(T, S, UT, US, nT, nS, thr2, lane);
+      nT = group_dot<E2, LOGLP>(T, T);
+      nS = group_dot<E2, LOGLP>(S, S);
+    }
+    // ---- stable descending rank among the NV vectors ----
+    int rT = 0, rS = 0;
+    {
+      const int pT = 2 * slot, pS = 2 * slot + 1;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float v = __shfl_sync(FULL, (j & 1) ? nS : nT, (j >> 1) << LOGLP);
+        rT += (v > nT) || (v == nT && j < pT);
+        rS += (v > nS) || (v == nS && j < pS);
+      }
+    }
+    const bool kT = act && nT > thr2 && rT < r_rt;
+    const bool kS = act && nS > thr2 && rS < r_rt;
+    if (io.sv) {
+      if (sub == 0 && act) {
+        if (rT < io.sv_width) io.sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
+        if (rS < io.sv_width) io.sv[rS] = nS > thr2 ? sqrtf(nS) : 0.f;
+      }
+      for (int k = NV + lane; k < io.sv_width; k += 32) io.sv[k] = 0.f;
+    }
+    if (io.sweeps && lane == 0) *io.sweeps = sweeps;
+
+    if constexpr (ROW) {
+      // A_n[(s,l), rank] = U-row element jj = 2l + s
+      if (act) {
+#pragma unroll
+        for (int e = 0; e < UEL; ++e) {
+          float lo, hi;
+          unpack2(UT[e / 2], lo, hi);
+          const float ut = (e & 1) ? hi : lo;
+          unpack2(US[e / 2], lo, hi);
+          const float us = (e & 1) ? hi : lo;
+          const int jj = sub * UEL + e;
+          const int l = jj >> 1, s = jj & 1;
+          if (jj < NV && l < b_rt) {
+            if (rT < r_rt) A[(s * b_rt + l) * r_rt + rT] = kT ? ut : 0.f;
+            if (rS < r_rt) A[(s * b_rt + l) * r_rt + rS] = kS ? us : 0.f;
+          }
+        }
+        // next Psi: row `rank` <- vector (zero when dropped)
 #pragma unroll
         for (int e = 0; e < EL; e += 4) {
           float4 t, s;
@@ -374,29 +378,22 @@ __device__ __forceinline__ float* run_step(const EncodeParams& P, const FastStep
           if (rS < R) *reinterpret_cast<float4*>(Pout + rS * Q + idx0 + e) = s;
         }
       }
-    }
-    __syncwarp();
-    return Pout;
-  }
-  // ---- column mode: normalise -> U; stage U as [e'][R] in Pout; A_n to global ----
-  {
-    const float iT = kT ? rsqrtf(nT) : 0.f;
-    const float iS = kS ? rsqrtf(nS) : 0.f;
-    if (act) {
+      __syncwarp();
+      return Pout;
+    } else {
+      // column mode: normalise -> U; stage U as [e'][R] in Pout; A_n to global
+      const float iT = kT ? rsqrtf(nT) : 0.f;
+      const float iS = kS ? rsqrtf(nS) : 0.f;
+      if (act) {
 #pragma unroll
-      for (int e = 0; e < EL; ++e) {
-        const int idx = idx0 + e;
-        float tv, sv_;
-        {
+        for (int e = 0; e < EL; ++e) {
+          const int idx = idx0 + e;
           float lo, hi;
           unpack2(T[e / 2], lo, hi);
-          tv = (e & 1) ? hi : lo;
+          const float uT = ((e & 1) ? hi : lo) * iT;
           unpack2(S[e / 2], lo, hi);
-          sv_ = (e & 1) ? hi : lo;
-        }
-        if (idx < LEN) {
-          const int s = idx >> st.logB, l = idx & (B - 1);
-          const float uT = tv * iT, uS = sv_ * iS;
+          const float uS = ((e & 1) ? hi : lo) * iS;
+          const int s = idx / B, l = idx % B;
           if (rT < R) Pout[idx * R + rT] = uT;
           if (rS < R) Pout[idx * R + rS] = uS;
           if (l < b_rt) {
@@ -405,117 +402,155 @@ __device__ __forceinline__ float* run_step(const EncodeParams& P, const FastStep
           }
         }
       }
-    }
-    __syncwarp();
-    if (n + 1 < P.L) {
-      switch (st.rpl) {
-        case 32: utm_product<32>(Pin, Pout, LEN, st.logB, st.logQ, R, lane); break;
-        case 16: utm_product<16>(Pin, Pout, LEN, st.logB, st.logQ, R, lane); break;
-        case 8: utm_product<8>(Pin, Pout, LEN, st.logB, st.logQ, R, lane); break;
-        case 4: utm_product<4>(Pin, Pout, LEN, st.logB, st.logQ, R, lane); break;
-        case 2: utm_product<2>(Pin, Pout, LEN, st.logB, st.logQ, R, lane); break;
-        default: utm_product<1>(Pin, Pout, LEN, st.logB, st.logQ, R, lane); break;
+      __syncwarp();
+      if constexpr (N + 1 < 10) {
+        // Psi_{n+1}[r][c] = sum_e U[e][r] M[e][c];  M[e = s*B + l][c] = Pin[l][s*Q + c]
+        constexpr int NG = Q >= 32 ? 1 : 32 / Q;   // lane groups sharing a column
+        constexpr int RPL = R >= NG ? R / NG : 1;   // rows per lane
+        const int c = lane % Q, g = lane / Q;
+        const bool active = g * RPL < R;
+        float acc[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) acc[i] = 0.f;
+        if (active) {
+#pragma unroll 4
+          for (int e = 0; e < LEN; ++e) {
+            const float m = Pin[(e % B) * 2 * Q + (e / B) * Q + c];
+            const float* u = Pout + e * R + g * RPL;
+            if constexpr (RPL % 4 == 0) {
+#pragma unroll
+              for (int i = 0; i < RPL; i += 4) {
+                const float4 uv = *reinterpret_cast<const float4*>(u + i);
+                acc[i] = fmaf(uv.x, m, acc[i]);
+                acc[i + 1] = fmaf(uv.y, m, acc[i + 1]);
+                acc[i + 2] = fmaf(uv.z, m, acc[i + 2]);
+                acc[i + 3] = fmaf(uv.w, m, acc[i + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < RPL; ++i) acc[i] = fmaf(u[i], m, acc[i]);
+            }
+          }
+        }
+        __syncwarp();
+        if (active) {
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) Pin[(g * RPL + i) * Q + c] = acc[i];
+        }
+        __syncwarp();
       }
+      return Pin;
     }
-    return Pin;
   }
 }
 
-__global__ void __launch_bounds__(128, 4)
-encode_fast_kernel(const __grid_constant__ EncodeParams P, const __grid_constant__ FastPlan plan) {
+// compile-time loop over steps N .. N1-1
+template <int DPAD, int N, int N1>
+__device__ __forceinline__ float* run_steps(const EncodeParams& P, int64_t img, float* mps, float* cur,
+                                            float* b0, float* b1, int lane) {
+  if constexpr (N < N1) {
+    StepIO io;
+    io.A = mps + P.site_off[N];
+    io.sv = P.svals_out ? reinterpret_cast<float*>(P.svals_out) + ((size_t)img * P.L + N) * P.sv_width : nullptr;
+    io.sweeps = P.sweeps_out ? P.sweeps_out + (size_t)img * P.L + N : nullptr;
+    io.b_rt = P.bonds[N];
+    io.r_rt = P.bonds[N + 1];
+    io.sv_width = P.sv_width;
+    float* next = jstep<DPAD, N>(P, img, io, cur, cur == b0 ? b1 : b0, lane);
+    return run_steps<DPAD, N + 1, N1>(P, img, mps, next, b0, b1, lane);
+  } else {
+    return cur;
+  }
+}
+
+// Kernel for steps [N0, N1).  ws_in: Psi_{N0} of every image ([B][2Q] floats,
+// image stride kWsStride) unless N0 == 0; ws_out: Psi_{N1} unless N1 == 10.
+constexpr int kWsStride = 1024;
+
+template <int DPAD, int N0, int N1>
+__global__ void __launch_bounds__(128) encode_steps_kernel(const __grid_constant__ EncodeParams P,
+                                                           const float* __restrict__ ws_in,
+                                                           float* __restrict__ ws_out) {
   extern __shared__ __align__(16) float smem_f[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* b0 = smem_f + (size_t)warp * 2048;
   float* b1 = b0 + 1024;
+  constexpr int IN_ELEMS = N0 > 0 ? Step<DPAD, cmin(N0, 9)>::B * 2 * Step<DPAD, cmin(N0, 9)>::Q : 0;
+  constexpr int OUT_ELEMS = N1 < 10 ? Step<DPAD, cmin(N1, 9)>::B * 2 * Step<DPAD, cmin(N1, 9)>::Q : 0;
   for (int64_t img = (int64_t)blockIdx.x * wpb + warp; img < P.N; img += (int64_t)gridDim.x * wpb) {
     float* mps = reinterpret_cast<float*>(P.mps_out) + (size_t)img * P.mps_stride;
-    float* cur = b0;
-#pragma unroll 1
-    for (int n = 0; n < OC_MAX_L; ++n) {
-      const FastStep& st = plan.st[n];
-      float* other = cur == b0 ? b1 : b0;
-      if (st.NV == 1) {
-        // last step: M (2B x 1) -> A = M / |M|; the 1x1 S.V is dropped (unit norm)
-        const int B = 1 << st.logB, LEN = 2 * B;
-        const int b_rt = P.bonds[n];
-        const int s = lane >> st.logB, l = lane & (B - 1);
-        const float v = lane < LEN ? cur[l * 2 + s] : 0.f;
-        const float nn = warp_sum(v * v);
-        const float inv = nn > 0.f ? rsqrtf(nn) : 0.f;
-        if (lane < LEN && l < b_rt) mps[P.site_off[n] + (s * b_rt + l)] = v * inv;
-        if (P.svals_out) {
-          float* sv = reinterpret_cast<float*>(P.svals_out) + ((size_t)img * P.L + n) * P.sv_width;
-          for (int k = lane; k < P.sv_width; k += 32) sv[k] = k == 0 ? sqrtf(nn) : 0.f;
-        }
-        if (P.sweeps_out && lane == 0) P.sweeps_out[(size_t)img * P.L + n] = 0;
-      } else if (st.el16) {
-        cur = run_step<16>(P, st, n, img, cur, other, mps, lane);
-      } else {
-        cur = run_step<4>(P, st, n, img, cur, other, mps, lane);
-      }
+    if constexpr (N0 > 0) {
+      const float4* src = reinterpret_cast<const float4*>(ws_in + (size_t)img * kWsStride);
+      float4* dst = reinterpret_cast<float4*>(b0);
+#pragma unroll
+      for (int i = lane; i < IN_ELEMS / 4; i += 32) dst[i] = __ldcs(src + i);
+      __syncwarp();
+    }
+    float* cur = run_steps<DPAD, N0, N1>(P, img, mps, b0, b0, b1, lane);
+    if constexpr (N1 < 10) {
+      __syncwarp();
+      const float4* src = reinterpret_cast<const float4*>(cur);
+      float4* dst = reinterpret_cast<float4*>(ws_out + (size_t)img * kWsStride);
+#pragma unroll
+      for (int i = lane; i < OUT_ELEMS / 4; i += 32) dst[i] = src[i];
     }
     __syncwarp();
   }
 }
 
-inline int ilog2(int x) {
-  int l = 0;
-  while ((1 << l) < x) ++l;
-  return l;
-}
-
 inline bool encode_fast_supported(const EncodeParams& P) { return P.L == 10; }
 
-// Build the per-step table for L = 10 and bond cap D (padded to a power of two).
-inline FastPlan encode_fast_plan(int D) {
-  FastPlan plan;
-  int DP = 1;
-  while (DP < D) DP <<= 1;
-  if (DP > 32) DP = 32;
-  auto bond = [&](int n) {
-    int b = 1 << (n < 10 - n ? n : 10 - n);
-    return b < DP ? b : DP;
-  };
-  for (int n = 0; n < 10; ++n) {
-    FastStep& s = plan.st[n];
-    const int B = bond(n), Q = 1 << (9 - n), Pp = 2 * B;
-    s.logB = ilog2(B);
-    s.logQ = ilog2(Q);
-    s.R = bond(n + 1);
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      // rows are the vectors when M_n is wide; second attempt falls back to
-      // columns if a lane cannot hold its share of the U row (4 elements)
-      s.row = (Pp < Q) && attempt == 0;
-      s.NV = s.row ? Pp : Q;
-      s.LEN = s.row ? Q : Pp;
-      s.M = s.NV / 2;
-      // EL = 16 when every slot gets >= 1 lane and at least half the warp is busy
-      int el = 16;
-      if (s.LEN < 16 || (s.LEN / 16) * s.M < 16) el = 4;
-      int lp = s.LEN / el;
-      if (lp < 1) lp = 1;
-      while (lp * s.M > 32) {  // more slots than lanes: longer chunks per lane
-        if (el == 4) { el = 16; lp = s.LEN / 16 > 0 ? s.LEN / 16 : 1; } else lp >>= 1;
-      }
-      s.el16 = el == 16;
-      s.logLP = ilog2(lp);
-      if (!s.row || 4 * lp >= s.NV) break;
-    }
-    const int ng = Q >= 32 ? 1 : 32 / Q;
-    s.rpl = s.R >= ng ? s.R / ng : 1;
-  }
-  return plan;
-}
-
-inline int encode_fast_launch(const EncodeParams& P, int sms, cudaStream_t st) {
+template <int DPAD, int N0, int N1>
+inline cudaError_t launch_steps(const EncodeParams& P, const float* ws_in, float* ws_out, int sms,
+                                cudaStream_t st) {
   const int warps = 4;
   const size_t smem = (size_t)warps * 2048 * sizeof(float);
   const int64_t need = (P.N + warps - 1) / warps;
   const int grid = (int)(need < (int64_t)sms * 16 ? need : (int64_t)sms * 16);
-  const FastPlan plan = encode_fast_plan(P.D);
-  encode_fast_kernel<<<grid, warps * 32, smem, st>>>(P, plan);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : (int)e;
+  encode_steps_kernel<DPAD, N0, N1><<<grid, warps * 32, smem, st>>>(P, ws_in, ws_out);
+  return cudaGetLastError();
+}
+
+template <int DPAD>
+inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, int sms, cudaStream_t st) {
+  cudaError_t e;
+  if ((e = launch_steps<DPAD, 0, 3>(P, nullptr, ws0, sms, st)) != cudaSuccess) return e;
+  if ((e = launch_steps<DPAD, 3, 4>(P, ws0, ws1, sms, st)) != cudaSuccess) return e;
+  if ((e = launch_steps<DPAD, 4, 5>(P, ws1, ws0, sms, st)) != cudaSuccess) return e;
+  if ((e = launch_steps<DPAD, 5, 6>(P, ws0, ws1, sms, st)) != cudaSuccess) return e;
+  return launch_steps<DPAD, 6, 10>(P, ws1, nullptr, sms, st);
+}
+
+constexpr int64_t kEncodeChunk = 32768;  // images per pass: 2 x 128 MB of Psi workspace
+constexpr int kEncodeLaunchesPerChunk = 5;
+
+// ws: 2 * min(N, kEncodeChunk) * kWsStride floats of device scratch.
+inline int encode_fast_launch(const EncodeParams& P0, float* ws, int sms, cudaStream_t st) {
+  int DP = 1;
+  while (DP < P0.D) DP <<= 1;
+  if (DP > 32) DP = 32;
+  const size_t in_esz = P0.in_dtype == 0 ? 4 : (P0.in_dtype == 1 ? 8 : 1);
+  const int64_t chunk = P0.N < kEncodeChunk ? P0.N : kEncodeChunk;
+  for (int64_t lo = 0; lo < P0.N; lo += kEncodeChunk) {
+    EncodeParams P = P0;
+    P.N = P0.N - lo < kEncodeChunk ? P0.N - lo : kEncodeChunk;
+    P.images = reinterpret_cast<const char*>(P0.images) + (size_t)lo * P0.ld * in_esz;
+    P.mps_out = reinterpret_cast<float*>(P0.mps_out) + (size_t)lo * P0.mps_stride;
+    if (P0.svals_out) P.svals_out = reinterpret_cast<float*>(P0.svals_out) + (size_t)lo * P0.L * P0.sv_width;
+    if (P0.sweeps_out) P.sweeps_out = P0.sweeps_out + (size_t)lo * P0.L;
+    float* ws0 = ws;
+    float* ws1 = ws + (size_t)chunk * kWsStride;
+    cudaError_t e;
+    switch (DP) {
+      case 32: e = launch_chain<32>(P, ws0, ws1, sms, st); break;
+      case 16: e = launch_chain<16>(P, ws0, ws1, sms, st); break;
+      case 8: e = launch_chain<8>(P, ws0, ws1, sms, st); break;
+      case 4: e = launch_chain<4>(P, ws0, ws1, sms, st); break;
+      default: e = launch_chain<2>(P, ws0, ws1, sms, st); break;  // D <= 2 (D = 1: all bonds 1)
+    }
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
 }
 
 }  // namespace oc
