@@ -71,7 +71,7 @@ struct Scratch {
   }
 };
 std::mutex g_mu, g_ws_mu;
-Scratch g_mps, g_img, g_clf, g_ov, g_am, g_enc_ws;
+Scratch g_mps, g_img, g_clf, g_ov, g_am, g_enc_ws, g_ov_ws;
 int g_force_generic = 0;
 
 template <typename K>
@@ -237,7 +237,13 @@ int oc_overlap_batch(const void* mps_dev, const int32_t* mps_bonds_host, const v
   P.argmax = argmax_out_dev;
 
   if (dtype == OC_F32 && !g_force_generic && oc::overlap_fast_supported(P)) {
-    int rc = oc::overlap_fast_launch(P, num_sms(), st);
+    float* ws = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(g_ws_mu);
+      if (int rc = g_ov_ws.ensure(oc::overlap_fast_scratch_floats(P) * sizeof(float))) return rc;
+      ws = reinterpret_cast<float*>(g_ov_ws.p);
+    }
+    int rc = oc::overlap_fast_launch(P, ws, num_sms(), st);
     if (rc == 0) return OC_OK;
     if (rc > 0) return fail(OC_E_CUDA, "overlap_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   }

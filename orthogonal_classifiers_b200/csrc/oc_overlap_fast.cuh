@@ -1,9 +1,368 @@
-// Specialised overlap kernel (fp32, classifier resident in shared memory).
-// Placeholder until the kernel lands.
+// Specialised overlap kernel (fp32): per image, left environment up to the
+// hairy site c, right environment down to it, centre contraction with the
+// label leg open (experiments.py:332-337), |.| and argmax fused.
+//
+// Persistent CTAs (one per SM).  A tiny prep kernel re-lays the classifier out
+// once per call:
+//   * every non-hairy site in the order the sweeps consume it — left sites
+//     [s][B][B'], right sites transposed [s][B'][B], rows padded to a multiple of
+//     4 floats — as ONE contiguous block that each CTA pulls into shared memory
+//     with a single bulk TMA copy (cp.async.bulk, SASS UBLKCP) + mbarrier;
+//   * the hairy site as Wc[(s,B,B')][label] so that the 16 label sums read it
+//     with coalesced 128-bit loads (it stays L1/L2 resident: 64 KB at D = 32).
+// One warp per image; every contraction is C[m][n] = sum_k Xt[k][m] Y[k][n] with
+// BOTH operands k-major in shared memory, so the inner loop is two LDS.128 and
+// sixteen FFMA per lane (4x4 register tile).
 #pragma once
 #include "oc_generic.cuh"
 
 namespace oc {
-inline bool overlap_fast_supported(const OverlapParams&) { return false; }
-inline int overlap_fast_launch(const OverlapParams&, int, cudaStream_t) { return -1; }
+
+constexpr int kOvMaxSmallW = 12288;  // floats of non-hairy classifier sites kept in smem
+constexpr int kOvMaxA = 3072;        // floats of one image's (padded) MPS in smem
+constexpr int kOvE = 1024;           // 32 x 32 environment
+constexpr int kOvT = 2048;           // 2 x 32 x 32 scratch
+constexpr int kOvR = 256;            // 16 x 16 right environment (x2, ping-pong)
+
+__host__ __device__ inline int r4(int x) { return (x + 3) & ~3; }
+
+struct OverlapFast {
+  int64_t w_off[OC_MAX_SITES];   // offset of site n inside the small-W block (floats); -1 for the hairy site
+  int64_t a_off[OC_MAX_SITES];   // offset of site n inside the per-warp MPS staging
+  int small_w_total;             // floats in the small-W block (multiple of 4)
+  int a_total;                   // floats of the per-warp MPS staging
+  int Spad;                      // label leg padded to a power of two >= 4
+  int64_t wc_elems;              // floats of the re-laid hairy site: 2 * B_c * r4(B_{c+1}) * Spad
+};
+
+// ---- classifier re-layout (one small launch per overlap call) --------------
+template <typename TIN>
+__global__ void overlap_prep_kernel(const TIN* __restrict__ clf, OverlapParams P, OverlapFast F,
+                                    float* __restrict__ small_w, float* __restrict__ wc) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int i = tid; i < F.small_w_total; i += nth) small_w[i] = 0.f;
+  for (int64_t i = tid; i < F.wc_elems; i += nth) wc[i] = 0.f;
+  // launched as ONE block (the buffers are < 150 KB), so a block barrier orders
+  // the zero fill before the scatter
+  __syncthreads();
+  for (int n = 0; n < P.L; ++n) {
+    const int Bl = P.B[n], Br = P.B[n + 1];
+    const TIN* W = clf + P.clf_off[n];
+    if (n == P.c) {
+      const int Br4 = r4(Br);
+      for (int i = tid; i < 2 * P.S * Bl * Br; i += nth) {
+        const int bp = i % Br, b = (i / Br) % Bl, l = (i / (Br * Bl)) % P.S, s = i / (Br * Bl * P.S);
+        wc[((int64_t)(s * Bl + b) * Br4 + bp) * F.Spad + l] = (float)W[i];
+      }
+    } else if (n < P.c) {
+      const int ld = r4(Br);
+      for (int i = tid; i < 2 * Bl * Br; i += nth) {
+        const int bp = i % Br, sb = i / Br;  // sb = s*Bl + b
+        small_w[F.w_off[n] + (int64_t)sb * ld + bp] = (float)W[i];
+      }
+    } else {
+      const int ld = r4(Bl);  // transposed: [s][B'][B]
+      for (int i = tid; i < 2 * Bl * Br; i += nth) {
+        const int bp = i % Br, b = (i / Br) % Bl, s = i / (Br * Bl);
+        small_w[F.w_off[n] + (int64_t)(s * Br + bp) * ld + b] = (float)W[i];
+      }
+    }
+  }
+}
+
+// C[m][n] = sum_{k<K} Xt[k*ldx + m] * Y[k*ldy + n], m < M, n < N.  4x4 tiles.
+// Reads may touch the (finite or not) padding up to r4(M), r4(N): such values
+// only reach accumulators that are never stored.
+__device__ __forceinline__ void mm_kmajor(float* __restrict__ C, int ldc, const float* __restrict__ Xt,
+                                          int ldx, const float* __restrict__ Y, int ldy, int M, int N,
+                                          int K, int lane) {
+  const int tm = (M + 3) >> 2, tn = (N + 3) >> 2, nt = tm * tn;
+  for (int t = lane; t < nt; t += 32) {
+    const int tj = t / tm, ti = t - tj * tm;
+    const float* xp = Xt + 4 * ti;
+    const float* yp = Y + 4 * tj;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float4 x = *reinterpret_cast<const float4*>(xp + k * ldx);
+      const float4 y = *reinterpret_cast<const float4*>(yp + k * ldy);
+      const float xv[4] = {x.x, x.y, x.z, x.w};
+      const float yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+    }
+    const int m0 = 4 * ti, n0 = 4 * tj;
+    if (n0 + 3 < N) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (m0 + i < M)
+          *reinterpret_cast<float4*>(C + (m0 + i) * ldc + n0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (m0 + i < M && n0 + j < N) C[(m0 + i) * ldc + n0 + j] = acc[i][j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_constant__ OverlapFast F,
+                    const float* __restrict__ small_w, const float* __restrict__ wc) {
+  extern __shared__ __align__(128) unsigned char smem_ov[];
+  float* sW = reinterpret_cast<float*>(smem_ov);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  constexpr int PER_WARP = kOvMaxA + kOvE + kOvT + 2 * kOvR;
+  float* wbase = sW + ((F.small_w_total + 31) & ~31) + (size_t)warp * PER_WARP;
+  float* As = wbase;
+  float* Eb = As + kOvMaxA;
+  float* Tb = Eb + kOvE;
+  float* Rb0 = Tb + kOvT;
+  float* Rb1 = Rb0 + kOvR;
+  __shared__ __align__(8) unsigned long long mbar;
+
+  // ---- one bulk TMA copy of the small classifier sites into shared memory ----
+  if (threadIdx.x == 0) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && F.small_w_total > 0) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&mbar);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(sW);
+    const unsigned bytes = (unsigned)F.small_w_total * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(small_w), "r"(bytes), "r"(bar)
+        : "memory");
+  }
+  if (F.small_w_total > 0) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&mbar);
+    unsigned done = 0;
+    for (int spin = 0; !done; ++spin) {
+      if (spin > (1 << 24)) __trap();  // a lost TMA completion must not hang the GPU
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+  }
+
+  const int c = P.c, L = P.L, S = P.S;
+  for (int64_t img = (int64_t)blockIdx.x * nwarps + warp; img < P.N; img += (int64_t)gridDim.x * nwarps) {
+    const float* mps = reinterpret_cast<const float*>(P.mps) + (size_t)img * P.mps_stride;
+    // ---- stage the image's sites: left sites [s][a][a'] (ld r4(a')), hairy
+    //      and right sites transposed [s][a'][a] (ld r4(a)) ----
+    for (int n = 0; n < L; ++n) {
+      const int al = P.a[n], ar = P.a[n + 1];
+      const float* A = mps + P.mps_off[n];
+      float* dst = As + F.a_off[n];
+      const int cnt = 2 * al * ar;
+      if (n < c) {
+        const int ld = r4(ar);
+        if (ld == ar) {
+          for (int i = lane; i < cnt; i += 32) dst[i] = __ldg(A + i);
+        } else {
+          for (int i = lane; i < cnt; i += 32) {
+            const int q = i / ar;
+            dst[q * ld + (i - q * ar)] = __ldg(A + i);
+          }
+        }
+      } else {
+        const int ld = r4(al);
+        for (int i = lane; i < cnt; i += 32) {
+          const int q = i / ar, ap = i - q * ar;  // q = s*al + a
+          const int s = q / al, a = q - s * al;
+          dst[(s * ar + ap) * ld + a] = __ldg(A + i);
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- left sweep.  State Et[B][a] (ld r4(a)); the last step leaves EL[a][B] ----
+    float* E = Eb;
+    if (lane == 0) E[0] = 1.f;
+    __syncwarp();
+    for (int n = 0; n < c; ++n) {
+      const int al = P.a[n], ar = P.a[n + 1], Bl = P.B[n], Br = P.B[n + 1];
+      const int ldE = r4(al), ldW = r4(Br), ldA = r4(ar), ldT = r4(Br);
+      const float* W = sW + F.w_off[n];
+      const float* A = As + F.a_off[n];
+      // T[(s,a)][B'] = sum_B Et[B][a] W[s][B][B']
+      for (int s = 0; s < 2; ++s)
+        mm_kmajor(Tb + s * al * ldT, ldT, E, ldE, W + s * Bl * ldW, ldW, al, Br, Bl, lane);
+      __syncwarp();
+      if (n + 1 < c) {
+        // Et'[B'][a'] = sum_(s,a) T[(s,a)][B'] A[(s,a)][a']
+        mm_kmajor(E, ldA, Tb, ldT, A, ldA, Br, ar, 2 * al, lane);
+      } else {
+        // EL[a'][B'] = sum_(s,a) A[(s,a)][a'] T[(s,a)][B']
+        mm_kmajor(E, ldT, A, ldA, Tb, ldT, ar, Br, 2 * al, lane);
+      }
+      __syncwarp();
+    }
+    // c == 0: EL = [[1]] already (ld irrelevant)
+
+    // ---- right sweep.  State R[a'][B'] (ld r4(B')) ----
+    float* R = Rb0;
+    float* R2 = Rb1;
+    if (lane == 0) R[0] = 1.f;
+    __syncwarp();
+    for (int n = L - 1; n > c; --n) {
+      const int al = P.a[n], ar = P.a[n + 1], Bl = P.B[n], Br = P.B[n + 1];
+      const int ldR = r4(Br), ldAt = r4(al), ldWt = r4(Bl), ldTp = r4(al);
+      const float* Wt = sW + F.w_off[n];  // [s][B'][B]
+      const float* At = As + F.a_off[n];  // [s][a'][a]
+      // T'[s][B'][a] = sum_a' R[a'][B'] At[s][a'][a]
+      for (int s = 0; s < 2; ++s)
+        mm_kmajor(Tb + s * Br * ldTp, ldTp, R, ldR, At + s * ar * ldAt, ldAt, Br, al, ar, lane);
+      __syncwarp();
+      // R'[a][B] = sum_(s,B') T'[(s,B')][a] Wt[(s,B')][B]
+      mm_kmajor(R2, ldWt, Tb, ldTp, Wt, ldWt, al, Bl, 2 * Br, lane);
+      __syncwarp();
+      float* t = R; R = R2; R2 = t;
+    }
+
+    // ---- hairy site ----
+    {
+      const int al = P.a[c], ar = P.a[c + 1], Bl = P.B[c], Br = P.B[c + 1];
+      const int ldAt = r4(al), ldR = r4(Br), ldG = r4(Br), ldEL = r4(Bl), ldH = r4(Br);
+      const float* At = As + F.a_off[c];  // [s][a'][a]
+      float* G = Tb;                      // [s][a][B']  (2 * al * ldG <= 1024)
+      float* H = Tb + 1024;               // [s][B][B']  (2 * Bl * ldH <= 1024)
+      // G[s][a][B'] = sum_a' At[s][a'][a] ER[a'][B']
+      for (int s = 0; s < 2; ++s) mm_kmajor(G + s * al * ldG, ldG, At + s * ar * ldAt, ldAt, R, ldR, al, Br, ar, lane);
+      __syncwarp();
+      // H[s][B][B'] = sum_a EL[a][B] G[s][a][B']
+      for (int s = 0; s < 2; ++s) mm_kmajor(H + s * Bl * ldH, ldH, E, ldEL, G + s * al * ldG, ldG, Bl, Br, al, lane);
+      __syncwarp();
+      // out[l] = sum_(s,B,B') Wc[(s,B,B')][l] H[s][B][B']; lane = (label quad, part)
+      const int lq_n = F.Spad >> 2;  // label quads (power of two <= 8)
+      const int lq = lane & (lq_n - 1), part = lane / lq_n, parts = 32 / lq_n;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const int rows = 2 * Bl;
+      for (int r = part; r < rows; r += parts) {
+        const float* hrow = H + r * ldH;
+        const float4* wrow = reinterpret_cast<const float4*>(wc + ((int64_t)r * ldH) * F.Spad) + lq;
+#pragma unroll 4
+        for (int bp = 0; bp < Br; ++bp) {
+          const float h = hrow[bp];
+          const float4 w = __ldg(wrow + bp * lq_n);
+          acc[0] = fmaf(w.x, h, acc[0]);
+          acc[1] = fmaf(w.y, h, acc[1]);
+          acc[2] = fmaf(w.z, h, acc[2]);
+          acc[3] = fmaf(w.w, h, acc[3]);
+        }
+      }
+      for (int o = lq_n; o < 32; o <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(FULL, acc[j], o);
+      }
+      // lanes 0 .. lq_n-1 hold labels 4 lq .. 4 lq + 3
+      float* ov = reinterpret_cast<float*>(P.overlaps) + (size_t)img * S;
+      float best = -1.f;
+      int besti = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int l = 4 * lq + j;
+        const float v = fabsf(acc[j]);
+        if (lane < lq_n && l < S) {
+          ov[l] = v;
+          if (v > best) { best = v; besti = l; }
+        }
+      }
+      if (P.argmax) {
+        // first index of the maximum over lanes 0 .. lq_n-1
+        for (int o = 1; o < lq_n; o <<= 1) {
+          const float ob = __shfl_xor_sync(FULL, best, o);
+          const int oi = __shfl_xor_sync(FULL, besti, o);
+          if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) P.argmax[img] = besti;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Host-side plan; returns false when the shapes do not fit the fast kernel.
+inline bool overlap_fast_plan(const OverlapParams& P, OverlapFast& F) {
+  if (P.L > OC_MAX_SITES || P.amax > 32 || P.Bmax > 32 || P.S > 32) return false;
+  int64_t w = 0, a = 0;
+  for (int n = 0; n < P.L; ++n) {
+    const int al = P.a[n], ar = P.a[n + 1], Bl = P.B[n], Br = P.B[n + 1];
+    F.a_off[n] = a;
+    a += (n < P.c) ? 2LL * al * r4(ar) : 2LL * ar * r4(al);
+    a = (a + 3) & ~3LL;
+    if (n == P.c) {
+      F.w_off[n] = -1;
+      // G and H live in the two halves of the scratch buffer
+      if (2 * al * r4(Br) > 1024 || 2 * Bl * r4(Br) > 1024) return false;
+    } else {
+      F.w_off[n] = w;
+      w += (n < P.c) ? 2LL * Bl * r4(Br) : 2LL * Br * r4(Bl);
+      w = (w + 3) & ~3LL;
+      // scratch T: left 2*al*r4(Br), right 2*Br*r4(al); env: E r4(al)*... <= 1024; R <= 256
+      if (n < P.c && (2 * al * r4(Br) > kOvT || Br * r4(ar) > kOvE || ar * r4(Br) > kOvE)) return false;
+      if (n > P.c && (2 * Br * r4(al) > kOvT || al * r4(Bl) > kOvR || ar * r4(Br) > kOvR)) return false;
+    }
+  }
+  if (w > kOvMaxSmallW || a > kOvMaxA) return false;
+  F.small_w_total = (int)w;
+  F.a_total = (int)a;
+  int sp = 4;
+  while (sp < P.S) sp <<= 1;
+  F.Spad = sp;
+  F.wc_elems = 2LL * P.B[P.c] * r4(P.B[P.c + 1]) * sp;
+  return true;
+}
+
+inline bool overlap_fast_supported(const OverlapParams& P) {
+  OverlapFast F;
+  return overlap_fast_plan(P, F);
+}
+
+// scratch_dev: at least (small_w_total + wc_elems) floats, 16-byte aligned.
+inline size_t overlap_fast_scratch_floats(const OverlapParams& P) {
+  OverlapFast F;
+  if (!overlap_fast_plan(P, F)) return 0;
+  return (size_t)((F.small_w_total + 31) & ~31) + (size_t)F.wc_elems;
+}
+
+inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int sms, cudaStream_t st) {
+  OverlapFast F;
+  if (!overlap_fast_plan(P, F)) return -1;
+  float* small_w = scratch_dev;
+  float* wc = scratch_dev + ((F.small_w_total + 31) & ~31);
+  overlap_prep_kernel<float><<<1, 1024, 0, st>>>(reinterpret_cast<const float*>(P.clf), P, F, small_w, wc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  constexpr int PER_WARP = kOvMaxA + kOvE + kOvT + 2 * kOvR;
+  const size_t wbytes = (size_t)((F.small_w_total + 31) & ~31) * 4;
+  int warps = 8;
+  while (warps > 1 && wbytes + (size_t)warps * PER_WARP * 4 > 220 * 1024) --warps;
+  const size_t smem = wbytes + (size_t)warps * PER_WARP * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(overlap_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int64_t need = (P.N + warps - 1) / warps;
+  const int grid = (int)(need < sms ? need : sms);
+  overlap_fast_kernel<<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 }  // namespace oc
