@@ -15,6 +15,7 @@ from .batched import (  # noqa: F401
     label_overlaps,
     set_force_generic,
 )
+from .distributed import all_reduce_counts, shard_bounds  # noqa: F401
 from .fMPO import fMPO  # noqa: F401
 from .tools import (  # noqa: F401
     data_to_QTN,

@@ -292,7 +292,8 @@ def evaluate(images, labels, classifier, D_encode: int | None = 32, dtype: str =
     _, am = classify_device(t, clf, D_encode)
     lab = torch.as_tensor(np.asarray(labels), dtype=torch.uint8).to(t.device)
     counts = count_correct(am, lab)
-    if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-        torch.distributed.all_reduce(counts)
+    if all_reduce:
+        from .distributed import all_reduce_counts
+        all_reduce_counts(counts)
     c = counts.cpu()
     return float(c[0].item()) / max(1, int(c[1].item()))
