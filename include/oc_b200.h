@@ -147,7 +147,8 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N,
 
 /* Diagnostics: peak-FMA microbenchmark kernel used by bench.py to measure the
  * fp32 FMA roofline denominator on the device it runs on.  Launches one
- * kernel of `iters` dependent-free FMA chains; returns flops executed. */
+ * kernel of `iters` dependent-free FMA chains; returns flops executed.
+ * iters < 0 runs |iters| iterations of the packed fma.rn.f32x2 variant. */
 int oc_fma_peak_launch(int64_t iters, float* sink_dev, double* flops_out,
                        void* stream);
 

@@ -405,11 +405,38 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int64_t iters, float* sin
   float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
   if (r == 123.456f) sink[0] = r;
 }
+__global__ void __launch_bounds__(256) fma2_peak_kernel(int64_t iters, float* sink) {
+  using oc::fma2;
+  using oc::pack2;
+  unsigned long long a0 = pack2(threadIdx.x * 1e-3f, 1.f), a1 = pack2(2.f, 3.f), a2 = pack2(4.f, 5.f),
+                     a3 = pack2(6.f, 7.f), a4 = pack2(8.f, 9.f), a5 = pack2(1.5f, 2.5f),
+                     a6 = pack2(3.5f, 4.5f), a7 = pack2(5.5f, 6.5f);
+  const unsigned long long m = pack2(0.999f, 0.999f), c = pack2(1e-3f, 1e-3f);
+  for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a0 = fma2(a0, m, c); a1 = fma2(a1, m, c); a2 = fma2(a2, m, c); a3 = fma2(a3, m, c);
+      a4 = fma2(a4, m, c); a5 = fma2(a5, m, c); a6 = fma2(a6, m, c); a7 = fma2(a7, m, c);
+    }
+  }
+  float lo, hi, r = 0.f;
+  oc::unpack2(a0, lo, hi); r += lo + hi; oc::unpack2(a1, lo, hi); r += lo + hi;
+  oc::unpack2(a2, lo, hi); r += lo + hi; oc::unpack2(a3, lo, hi); r += lo + hi;
+  oc::unpack2(a4, lo, hi); r += lo + hi; oc::unpack2(a5, lo, hi); r += lo + hi;
+  oc::unpack2(a6, lo, hi); r += lo + hi; oc::unpack2(a7, lo, hi); r += lo + hi;
+  if (r == 123.456f) sink[0] = r;
+}
 }  // namespace
 
 int oc_fma_peak_launch(int64_t iters, float* sink_dev, double* flops_out, void* stream) {
   const int threads = 256;
   const int grid = num_sms() * 8;
+  if (iters < 0) {  // negative iteration count selects the packed f32x2 (FFMA2) variant
+    fma2_peak_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(-iters, sink_dev);
+    OC_CUDA(cudaGetLastError());
+    if (flops_out) *flops_out = 2.0 * 64.0 * (double)(-iters) * threads * grid;
+    return OC_OK;
+  }
   fma_peak_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(iters, sink_dev);
   OC_CUDA(cudaGetLastError());
   if (flops_out) *flops_out = 2.0 * 64.0 * (double)iters * threads * grid;

@@ -23,6 +23,7 @@ constexpr int kOvMaxA = 3072;        // floats of one image's (padded) MPS in sm
 constexpr int kOvE = 1024;           // 32 x 32 environment
 constexpr int kOvT = 2048;           // 2 x 32 x 32 scratch
 constexpr int kOvR = 256;            // 16 x 16 right environment (x2, ping-pong)
+constexpr int kOvPre = 22;           // float4 prefetch registers per lane: images of <= 22*128 floats
 
 __host__ __device__ inline int r4(int x) { return (x + 3) & ~3; }
 
@@ -159,33 +160,60 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
   }
 
   const int c = P.c, L = P.L, S = P.S;
-  for (int64_t img = (int64_t)blockIdx.x * nwarps + warp; img < P.N; img += (int64_t)gridDim.x * nwarps) {
+  // ---- per-CTA staging table: element e of an image block -> offset in As.
+  //      left sites keep [s][a][a'] (ld r4(a')), hairy and right sites are
+  //      transposed to [s][a'][a] (ld r4(a)) ----
+  unsigned short* tab = reinterpret_cast<unsigned short*>(sW + ((F.small_w_total + 31) & ~31) +
+                                                          (size_t)nwarps * PER_WARP);
+  const int stride = (int)P.mps_stride;
+  for (int e = threadIdx.x; e < stride; e += blockDim.x) {
+    int n = 0;
+    while (n + 1 < L && e >= (int)P.mps_off[n + 1]) ++n;
+    const int i = e - (int)P.mps_off[n];
+    const int al = P.a[n], ar = P.a[n + 1];
+    const int q = i / ar, ap = i - q * ar;  // q = s*al + a
+    int d;
+    if (n < c) {
+      d = q * r4(ar) + ap;
+    } else {
+      const int sdx = q / al, a = q - sdx * al;
+      d = (sdx * ar + ap) * r4(al) + a;
+    }
+    tab[e] = (unsigned short)(F.a_off[n] + d);
+  }
+  __syncthreads();
+  // vector path: whole image block = `stride` floats, 16-byte aligned, <= kOvPre*128
+  const bool vec = (stride & 3) == 0 && stride <= kOvPre * 128 &&
+                   ((reinterpret_cast<uintptr_t>(P.mps) & 15) == 0);
+  float4 pre[kOvPre];
+  auto prefetch = [&](int64_t im) {
+    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.mps) + (size_t)im * stride);
+#pragma unroll
+    for (int j = 0; j < kOvPre; ++j) {
+      const int v = lane + 32 * j;
+      if (4 * v < stride) pre[j] = __ldcs(src + v);
+    }
+  };
+  int64_t img = (int64_t)blockIdx.x * nwarps + warp;
+  if (vec && img < P.N) prefetch(img);
+  for (; img < P.N; img += (int64_t)gridDim.x * nwarps) {
     const float* mps = reinterpret_cast<const float*>(P.mps) + (size_t)img * P.mps_stride;
-    // ---- stage the image's sites: left sites [s][a][a'] (ld r4(a')), hairy
-    //      and right sites transposed [s][a'][a] (ld r4(a)) ----
-    for (int n = 0; n < L; ++n) {
-      const int al = P.a[n], ar = P.a[n + 1];
-      const float* A = mps + P.mps_off[n];
-      float* dst = As + F.a_off[n];
-      const int cnt = 2 * al * ar;
-      if (n < c) {
-        const int ld = r4(ar);
-        if (ld == ar) {
-          for (int i = lane; i < cnt; i += 32) dst[i] = __ldg(A + i);
-        } else {
-          for (int i = lane; i < cnt; i += 32) {
-            const int q = i / ar;
-            dst[q * ld + (i - q * ar)] = __ldg(A + i);
-          }
-        }
-      } else {
-        const int ld = r4(al);
-        for (int i = lane; i < cnt; i += 32) {
-          const int q = i / ar, ap = i - q * ar;  // q = s*al + a
-          const int s = q / al, a = q - s * al;
-          dst[(s * ar + ap) * ld + a] = __ldg(A + i);
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < kOvPre; ++j) {
+        const int v = lane + 32 * j;
+        if (4 * v < stride) {
+          const uint2 t = *reinterpret_cast<const uint2*>(tab + 4 * v);
+          As[t.x & 0xffff] = pre[j].x;
+          As[t.x >> 16] = pre[j].y;
+          As[t.y & 0xffff] = pre[j].z;
+          As[t.y >> 16] = pre[j].w;
         }
       }
+      const int64_t nxt = img + (int64_t)gridDim.x * nwarps;
+      if (nxt < P.N) prefetch(nxt);  // in flight during this image's contractions
+    } else {
+      for (int e = lane; e < stride; e += 32) As[tab[e]] = __ldg(mps + e);
     }
     __syncwarp();
 
@@ -254,7 +282,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       for (int r = part; r < rows; r += parts) {
         const float* hrow = H + r * ldH;
         const float4* wrow = reinterpret_cast<const float4*>(wc + ((int64_t)r * ldH) * F.Spad) + lq;
-#pragma unroll 4
+#pragma unroll 16
         for (int bp = 0; bp < Br; ++bp) {
           const float h = hrow[bp];
           const float4 w = __ldg(wrow + bp * lq_n);
@@ -317,7 +345,7 @@ inline bool overlap_fast_plan(const OverlapParams& P, OverlapFast& F) {
       if (n > P.c && (2 * Br * r4(al) > kOvT || al * r4(Bl) > kOvR || ar * r4(Br) > kOvR)) return false;
     }
   }
-  if (w > kOvMaxSmallW || a > kOvMaxA) return false;
+  if (w > kOvMaxSmallW || a > kOvMaxA || a > 65535 || P.mps_stride > 16384) return false;
   F.small_w_total = (int)w;
   F.a_total = (int)a;
   int sp = 4;
@@ -349,9 +377,10 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   if (e != cudaSuccess) return (int)e;
   constexpr int PER_WARP = kOvMaxA + kOvE + kOvT + 2 * kOvR;
   const size_t wbytes = (size_t)((F.small_w_total + 31) & ~31) * 4;
+  const size_t tabbytes = (((size_t)P.mps_stride * 2 + 15) & ~(size_t)15) + 16;
   int warps = 8;
-  while (warps > 1 && wbytes + (size_t)warps * PER_WARP * 4 > 220 * 1024) --warps;
-  const size_t smem = wbytes + (size_t)warps * PER_WARP * 4;
+  while (warps > 1 && wbytes + tabbytes + (size_t)warps * PER_WARP * 4 > 222 * 1024) --warps;
+  const size_t smem = wbytes + tabbytes + (size_t)warps * PER_WARP * 4;
   static bool attr_set = false;
   if (!attr_set) {
     e = cudaFuncSetAttribute(overlap_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
