@@ -7,6 +7,7 @@ from . import synthetic  # noqa: F401
 from ._lib import OcError  # noqa: F401
 from .batched import (  # noqa: F401
     DeviceClassifier,
+    HostPipeline,
     MPSBatch,
     classify,
     count_correct,

@@ -247,6 +247,50 @@ def classify_device(images_dev: torch.Tensor, clf: DeviceClassifier, D: int | No
     return ov, am
 
 
+class HostPipeline:
+    """End-to-end encode + classify for HOST-resident images: the batch is cut
+    into chunks; the pinned-host -> device copy of chunk k+1 runs on a copy
+    stream while the kernels of chunk k run on the compute stream, and the
+    results return to pinned host buffers asynchronously.  Device staging is
+    allocated once and reused across calls."""
+
+    def __init__(self, clf: DeviceClassifier, n_pix: int, D: int | None, chunk: int = 17_500,
+                 in_dtype=torch.float32):
+        self.clf, self.D, self.chunk, self.n_pix = clf, D, int(chunk), n_pix
+        dev = clf.device
+        self.dev = dev
+        L = n_sites_for(n_pix)
+        _, offs = mps_layout(L, D)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.stage = [torch.empty((self.chunk, n_pix), dtype=in_dtype, device=dev) for _ in range(2)]
+        self.ws = torch.empty((self.chunk, offs[-1]), dtype=_TORCH_DT[clf.dtype], device=dev)
+        self.ov = [torch.empty((self.chunk, clf.S), dtype=_TORCH_DT[clf.dtype], device=dev) for _ in range(2)]
+        self.am = [torch.empty((self.chunk,), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.freed = [torch.cuda.Event() for _ in range(2)]
+
+    def run(self, images_host: torch.Tensor, ov_host: torch.Tensor, am_host: torch.Tensor) -> None:
+        """images_host (N, n_pix) pinned; ov_host (N, S), am_host (N,) pinned.
+        Returns after the results are on the host."""
+        N = images_host.shape[0]
+        comp = torch.cuda.current_stream(self.dev)
+        for k, lo in enumerate(range(0, N, self.chunk)):
+            hi = min(N, lo + self.chunk)
+            b = k & 1
+            with torch.cuda.stream(self.copy_stream):
+                if k >= 2:
+                    self.copy_stream.wait_event(self.freed[b])  # kernels of chunk k-2 done with this buffer
+                self.stage[b][: hi - lo].copy_(images_host[lo:hi], non_blocking=True)
+                self.copied[b].record(self.copy_stream)
+            comp.wait_event(self.copied[b])
+            classify_device(self.stage[b][: hi - lo], self.clf, self.D, workspace=self.ws,
+                            out=(self.ov[b][: hi - lo], self.am[b][: hi - lo]))
+            self.freed[b].record(comp)
+            ov_host[lo:hi].copy_(self.ov[b][: hi - lo], non_blocking=True)
+            am_host[lo:hi].copy_(self.am[b][: hi - lo], non_blocking=True)
+        comp.synchronize()
+
+
 def label_overlaps(images_or_mps, classifier, D_encode: int | None = 32, dtype: str = "f32",
                    device=None) -> np.ndarray:
     """The reference's inline prediction expression, batched:

@@ -223,3 +223,20 @@ def test_generic_and_specialised_kernels_agree(gpu_lib):
         assert np.abs(sf - sg).max() <= 1e-5 * sg.max()
         if D == 32:
             assert np.abs(ov_fast - ov_gen).max() <= 1e-5 * ov_gen.max()
+
+
+def test_host_pipeline_matches_single_shot(gpu_lib):
+    """Chunked, copy/compute-overlapped host API == one-shot classify, bit-exact."""
+    import torch
+    imgs = synthetic_images(1000, seed=31).astype(np.float32)
+    clf = gpu_lib.DeviceClassifier(random_classifier(10, 32, centre=5, seed=2))
+    ref_ov, ref_am = gpu_lib.classify(imgs, clf, 32)
+    pipe = gpu_lib.HostPipeline(clf, 784, 32, chunk=300)
+    pin = torch.from_numpy(imgs).pin_memory()
+    ov = torch.empty((1000, 16), dtype=torch.float32).pin_memory()
+    am = torch.empty((1000,), dtype=torch.int32).pin_memory()
+    for _ in range(2):
+        ov.zero_(); am.zero_()
+        pipe.run(pin, ov, am)
+        np.testing.assert_array_equal(ov.numpy().astype(np.float64), ref_ov)
+        np.testing.assert_array_equal(am.numpy(), ref_am)
