@@ -281,8 +281,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(N * 784 * 4),
                     "d2h_bytes_per_step": int(N * (16 * 4 + 4))},
-            # per step: 5 encode kernels per 32,768-image chunk + overlap prep + overlap + count
-            "gpu_launches": (5 * ((N + 32767) // 32768) + 3) * args.steps,
+            # per step: 5 encode kernels per 131,072-image chunk + overlap prep + overlap + count
+            "gpu_launches": (5 * ((N + 131071) // 131072) + 3) * args.steps,
             "kernels_ms": {"encode": enc_ms, "overlap": ovl_ms},
             "roofline": {"bound": "fp32_fma", "kernel": "encode", "achieved": enc_tflops, "peak": best,
                          "unit": "TFLOP/s", "frac": enc_tflops / best if best else None, "traffic": None,

@@ -96,6 +96,10 @@ int oc_set_option(const char* key, int value) {
     g_force_generic = value;
     return OC_OK;
   }
+  if (key && !strcmp(key, "enc_warps") && value >= 1 && value <= 4) {
+    oc::encode_warps_per_cta() = value;
+    return OC_OK;
+  }
   return fail(OC_E_ARG, "unknown option %s", key ? key : "(null)");
 }
 

@@ -135,18 +135,23 @@ __device__ __forceinline__ void rotate_pair(u64 (&a)[E2], u64 (&b)[E2], u64 (&ua
   const float ab2 = ab * ab;
   const bool rot = (ab2 > kTol2 * d) && (aa > thr2) && (bb > thr2) && !idle;
   again = again || (rot && ab2 > kQStop2 * d);
-  // branch-free; the MUFU approximations only influence how well this rotation
-  // orthogonalises the pair, never its orthogonality (c, s are renormalised)
-  const float two_ab = rot ? ab + ab : 1.f;
-  const float zeta = (bb - aa) * rcp_approx(two_ab);
-  float t = rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.f)));
-  t = rot ? copysignf(t, zeta) : 0.f;
-  const float h = fmaf(t, t, 1.f);
-  float r = rsqrt_approx(h);
-  r = r * fmaf(-0.5f * h, r * r, 1.5f);  // Newton step: c^2 + s^2 = 1 to ~1 ulp
+  // Branch-free rotation parameters with only two dependent MUFUs.  With
+  // delta = bb - aa, gamma = 2 ab, w = sqrt(delta^2 + gamma^2), den = |delta| + w:
+  //   tan = sgn(delta) gamma / den,  cos = den q,  sin = sgn(delta) gamma q,
+  //   q = (den^2 + gamma^2)^(-1/2)   (one Newton step -> c^2 + s^2 = 1 to ~1 ulp,
+  // whatever the error of the approximate sqrt).  |theta| <= pi/4.
+  const float delta = bb - aa;
+  const float gamma = rot ? ab + ab : 0.f;
+  const float w = sqrt_approx(fmaf(delta, delta, gamma * gamma));
+  const float den = fabsf(delta) + w;
+  const float sg = copysignf(gamma, delta * gamma);  // sgn(delta) * gamma  (sgn(0) = +)
+  const float X = fmaf(den, den, gamma * gamma);
+  float q = rsqrt_approx(X);
+  q = q * fmaf(-0.5f * X, q * q, 1.5f);
+  const float t = rot ? sg * rcp_approx(den) : 0.f;
   // idle: both vectors stay where they are (the second picks up a sign)
-  const float c = idle ? 0.f : r;
-  const float s = idle ? 1.f : r * t;
+  const float c = idle ? 0.f : (rot ? den * q : 1.f);
+  const float s = idle ? 1.f : (rot ? sg * q : 0.f);
   // |a'|^2 = aa - t ab, |b'|^2 = bb + t ab; positions swap
   float n_first = idle ? aa : fmaf(t, ab, bb);
   float n_second = idle ? bb : fmaf(-t, ab, aa);
@@ -188,7 +193,7 @@ __device__ __forceinline__ int jacobi_regs(u64 (&T)[E2], u64 (&S)[E2], u64 (&UT)
     bool again = false;
     nT = group_dot<E2, LOGLP>(T, T);
     nS = group_dot<E2, LOGLP>(S, S);
-#pragma unroll 1
+#pragma unroll 2
     for (int rr = 0; rr < M; ++rr) {
       rotate_pair<E2, U2, LOGLP, ROW>(T, S, UT, US, nT, nS, thr2, false, again);
       if (M > 1) {
@@ -468,7 +473,7 @@ __device__ __forceinline__ float* run_steps(const EncodeParams& P, int64_t img, 
 constexpr int kWsStride = 1024;
 
 template <int DPAD, int N0, int N1>
-__global__ void __launch_bounds__(128) encode_steps_kernel(const __grid_constant__ EncodeParams P,
+__global__ void __launch_bounds__(128, 6) encode_steps_kernel(const __grid_constant__ EncodeParams P,
                                                            const float* __restrict__ ws_in,
                                                            float* __restrict__ ws_out) {
   extern __shared__ __align__(16) float smem_f[];
@@ -500,13 +505,21 @@ __global__ void __launch_bounds__(128) encode_steps_kernel(const __grid_constant
 
 inline bool encode_fast_supported(const EncodeParams& P) { return P.L == 10; }
 
+inline int& encode_warps_per_cta() {
+  static int w = 4;
+  return w;
+}
+
 template <int DPAD, int N0, int N1>
 inline cudaError_t launch_steps(const EncodeParams& P, const float* ws_in, float* ws_out, int sms,
                                 cudaStream_t st) {
-  const int warps = 4;
+  const int warps = encode_warps_per_cta();
   const size_t smem = (size_t)warps * 2048 * sizeof(float);
+  // one image per warp, one CTA per 4 images: per-image cost varies with the
+  // sweep count, so the hardware CTA scheduler does the load balancing
   const int64_t need = (P.N + warps - 1) / warps;
-  const int grid = (int)(need < (int64_t)sms * 16 ? need : (int64_t)sms * 16);
+  const int grid = (int)need;
+  (void)sms;
   encode_steps_kernel<DPAD, N0, N1><<<grid, warps * 32, smem, st>>>(P, ws_in, ws_out);
   return cudaGetLastError();
 }
@@ -521,7 +534,7 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, i
   return launch_steps<DPAD, 6, 10>(P, ws1, nullptr, sms, st);
 }
 
-constexpr int64_t kEncodeChunk = 32768;  // images per pass: 2 x 128 MB of Psi workspace
+constexpr int64_t kEncodeChunk = 131072;  // images per pass: 2 x 512 MB of Psi workspace
 constexpr int kEncodeLaunchesPerChunk = 5;
 
 // ws: 2 * min(N, kEncodeChunk) * kWsStride floats of device scratch.
