@@ -103,6 +103,11 @@ struct Step {
   static_assert(!ROW || UEL * LP >= NV, "U row does not fit");
 };
 
+#ifdef OC_DEBUG_COUNTERS
+static __device__ int g_dbg_lost_dummy;
+#define g_dbg_lost (*dbg_lost_ptr())
+__device__ __forceinline__ int* dbg_lost_ptr() { extern __shared__ __align__(16) float smem_dbg[]; return reinterpret_cast<int*>(smem_dbg + 4 * 2048) + (threadIdx.x >> 5); }
+#endif
 template <int E2, int LOGLP>
 __device__ __forceinline__ float group_dot(const u64 (&a)[E2], const u64 (&b)[E2]) {
   // independent partial sums keep the FFMA2 dependency chains short
@@ -172,6 +177,9 @@ __device__ __forceinline__ void rotate_pair(u64 (&a)[E2], u64 (&b)[E2], u64 (&ua
     }
   }
   if (__any_sync(FULL, lost)) {  // warp-uniform, rare after the first sweeps
+#ifdef OC_DEBUG_COUNTERS
+    ++g_dbg_lost;
+#endif
     n_first = group_dot<E2, LOGLP>(a, a);
     n_second = group_dot<E2, LOGLP>(b, b);
   }
@@ -179,14 +187,18 @@ __device__ __forceinline__ void rotate_pair(u64 (&a)[E2], u64 (&b)[E2], u64 (&ua
   nb = n_second;
 }
 
+// `mlive` (warp-uniform, 1..M): only slots [0, mlive) hold non-zero vectors
+// (rows of Psi_n dropped by the previous step are exactly zero and sit at the
+// end), so the odd-even line is cut to 2*mlive positions: a sweep is 2*mlive
+// rounds instead of 2*M.
 template <int E2, int U2, int LOGLP, int M, bool ROW>
 __device__ __forceinline__ int jacobi_regs(u64 (&T)[E2], u64 (&S)[E2], u64 (&UT)[U2], u64 (&US)[U2],
-                                           float& nT, float& nS, float thr2, int lane) {
+                                           float& nT, float& nS, float thr2, int lane, int mlive) {
   constexpr int LP = 1 << LOGLP;
   const int slot = lane >> LOGLP;
   const int src_dn = (lane + LP) & 31;
   const int src_up = (lane - LP) & 31;
-  const bool idleB = slot >= M - 1;
+  const bool idleB = slot >= mlive - 1;
   int sweeps = 0;
 #pragma unroll 1
   while (sweeps < kMaxSweeps) {
@@ -194,7 +206,7 @@ __device__ __forceinline__ int jacobi_regs(u64 (&T)[E2], u64 (&S)[E2], u64 (&UT)
     nT = group_dot<E2, LOGLP>(T, T);
     nS = group_dot<E2, LOGLP>(S, S);
 #pragma unroll 2
-    for (int rr = 0; rr < M; ++rr) {
+    for (int rr = 0; rr < mlive; ++rr) {
       rotate_pair<E2, U2, LOGLP, ROW>(T, S, UT, US, nT, nS, thr2, false, again);
       if (M > 1) {
         u64 R[E2], UR[U2];
@@ -214,7 +226,7 @@ __device__ __forceinline__ int jacobi_regs(u64 (&T)[E2], u64 (&S)[E2], u64 (&UT)
       }
     }
     ++sweeps;
-    if (M == 1) break;  // one rotation orthogonalises two vectors exactly
+    if (M == 1 || mlive == 1) break;  // one rotation orthogonalises two vectors exactly
     if (!__any_sync(FULL, again)) break;
   }
   return sweeps;
@@ -327,8 +339,19 @@ __device__ __forceinline__ float* jstep(const EncodeParams& P, int64_t img, cons
     const float thr2 = kFloor2 * fro;
 
     int sweeps = 0;
+#ifdef OC_DEBUG_COUNTERS
+    int dbg_mlive = 0;
+    if (lane == 0) g_dbg_lost = 0;
+    __syncwarp();
+#endif
     if (fro > 0.f) {
-      sweeps = jacobi_regs<E2, U2, LOGLP, M, ROW>(T, S, UT, US, nT, nS, thr2, lane);
+      // highest slot holding a non-zero vector (exact zeros: padding / dropped rows)
+      const unsigned livemask = __ballot_sync(FULL, act && (nT + nS) > 0.f);
+      const int mlive = M == 1 ? 1 : ((31 - __clz(livemask)) >> LOGLP) + 1;
+#ifdef OC_DEBUG_COUNTERS
+      dbg_mlive = mlive;
+#endif
+      sweeps = jacobi_regs<E2, U2, LOGLP, M, ROW>(T, S, UT, US, nT, nS, thr2, lane, mlive);
       nT = group_dot<E2, LOGLP>(T, T);
       nS = group_dot<E2, LOGLP>(S, S);
     }
@@ -352,7 +375,11 @@ __device__ __forceinline__ float* jstep(const EncodeParams& P, int64_t img, cons
       }
       for (int k = NV + lane; k < io.sv_width; k += 32) io.sv[k] = 0.f;
     }
+#ifdef OC_DEBUG_COUNTERS
+    if (io.sweeps && lane == 0) { *io.sweeps = sweeps + 100 * dbg_mlive + 10000 * g_dbg_lost; g_dbg_lost = 0; }
+#else
     if (io.sweeps && lane == 0) *io.sweeps = sweeps;
+#endif
 
     if constexpr (ROW) {
       // A_n[(s,l), rank] = U-row element jj = 2l + s
@@ -514,7 +541,11 @@ template <int DPAD, int N0, int N1>
 inline cudaError_t launch_steps(const EncodeParams& P, const float* ws_in, float* ws_out, int sms,
                                 cudaStream_t st) {
   const int warps = encode_warps_per_cta();
+#ifdef OC_DEBUG_COUNTERS
+  const size_t smem = (size_t)4 * 2048 * sizeof(float) + 64;
+#else
   const size_t smem = (size_t)warps * 2048 * sizeof(float);
+#endif
   // one image per warp, one CTA per 4 images: per-image cost varies with the
   // sweep count, so the hardware CTA scheduler does the load balancing
   const int64_t need = (P.N + warps - 1) / warps;
