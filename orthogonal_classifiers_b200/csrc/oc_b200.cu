@@ -15,6 +15,7 @@
 
 #include "oc_generic.cuh"
 #include "oc_encode_fast.cuh"
+#include "oc_encode_hw.cuh"
 #include "oc_overlap_fast.cuh"
 
 namespace {
@@ -94,6 +95,10 @@ const char* oc_last_error(void) { return g_err.c_str(); }
 int oc_set_option(const char* key, int value) {
   if (key && !strcmp(key, "force_generic")) {
     g_force_generic = value;
+    return OC_OK;
+  }
+  if (key && !strcmp(key, "enc_hw")) {
+    oc::encode_use_hw() = value;
     return OC_OK;
   }
   if (key && !strcmp(key, "enc_warps") && value >= 1 && value <= 4) {

@@ -568,6 +568,15 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, i
 constexpr int64_t kEncodeChunk = 131072;  // images per pass: 2 x 512 MB of Psi workspace
 constexpr int kEncodeLaunchesPerChunk = 5;
 
+inline int& encode_use_hw() {
+  static int v = 1;
+  return v;
+}
+namespace hw {
+inline bool supported(const EncodeParams& P);
+inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, int sms, cudaStream_t st);
+}  // namespace hw
+
 // ws: 2 * min(N, kEncodeChunk) * kWsStride floats of device scratch.
 inline int encode_fast_launch(const EncodeParams& P0, float* ws, int sms, cudaStream_t st) {
   int DP = 1;
@@ -585,6 +594,11 @@ inline int encode_fast_launch(const EncodeParams& P0, float* ws, int sms, cudaSt
     float* ws0 = ws;
     float* ws1 = ws + (size_t)chunk * kWsStride;
     cudaError_t e;
+    if (encode_use_hw() && hw::supported(P)) {
+      e = hw::launch_chain(P, ws0, ws1, sms, st);
+      if (e != cudaSuccess) return (int)e;
+      continue;
+    }
     switch (DP) {
       case 32: e = launch_chain<32>(P, ws0, ws1, sms, st); break;
       case 16: e = launch_chain<16>(P, ws0, ws1, sms, st); break;
