@@ -42,6 +42,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
         "-o", LIB, os.path.join(CSRC, "oc_b200.cu"),
     ]
+    cmd += os.environ.get("OC_NVCC_EXTRA", "").split()  # experiments only (e.g. -DOC_HW_MINB=5)
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

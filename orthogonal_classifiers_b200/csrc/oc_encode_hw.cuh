@@ -72,7 +72,7 @@ __device__ __forceinline__ float dot16(const u64 (&a)[16], const u64 (&b)[16]) {
 // never depends on which image shares its warp.
 template <int LOGLP>
 __device__ __forceinline__ void rotate16(u64 (&a)[16], u64 (&b)[16], float& na, float& nb, float thr2,
-                                         bool hold, unsigned hmask, bool& again) {
+                                         bool hold, bool& lostf, bool& again) {
   const float ab = dot16<LOGLP>(a, b);
   const float aa = na, bb = nb;
   const float d = aa * bb;
@@ -94,21 +94,16 @@ __device__ __forceinline__ void rotate16(u64 (&a)[16], u64 (&b)[16], float& na, 
   const float ns = hold ? 1.f : -s;
   float n_first = hold ? aa : fmaf(t, ab, bb);
   float n_second = hold ? bb : fmaf(-t, ab, aa);
-  const bool lost = rot && (n_second < kCancel * aa || n_first < kCancel * bb);
+  // a norm update that cancelled is refreshed from the data at the end of the
+  // round pair (jacobi16); until then the stale value only makes one rotation
+  // less effective, never wrong (c and s stay consistent)
+  lostf = lostf || (rot && (n_second < kCancel * aa || n_first < kCancel * bb));
   const u64 c2 = pack2(c, c), s2 = pack2(s, s), ns2 = pack2(ns, ns);
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     const u64 x = a[e], y = b[e];
     a[e] = fma2(s2, x, mul2(c2, y));
     b[e] = fma2(c2, x, mul2(ns2, y));
-  }
-  const unsigned lostmask = __ballot_sync(FULL, lost);
-  if (lostmask) {  // warp-uniform, rare after the first sweeps
-    const float f1 = dot16<LOGLP>(a, a), f2 = dot16<LOGLP>(b, b);
-    if (lostmask & hmask) {  // only the half that cancelled takes the refreshed norms
-      n_first = f1;
-      n_second = f2;
-    }
   }
   na = n_first;
   nb = n_second;
@@ -177,6 +172,10 @@ __device__ __forceinline__ void frot16(u64 (&a)[16], u64 (&b)[16], float& na, fl
 #ifndef OC_HW_FAST_ROT
 #define OC_HW_FAST_ROT 0
 #endif
+#ifndef OC_HW_UNROLL
+#define OC_HW_UNROLL 1
+#endif
+constexpr int kHwUnroll = OC_HW_UNROLL;
 template <int LOGLP>
 __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, float& nS, float thr2,
                                         int lane, int mlive, int mlive_max) {
@@ -196,6 +195,7 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
 #pragma unroll 1
   for (int sw = 0; sw < kMaxSweeps; ++sw) {
     bool again = false;
+    bool lostf = false;
     {
 #if OC_HW_FAST_ROT
       // fold the scale factors back into the data before refreshing the norms
@@ -213,13 +213,13 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
         nS = fS;
       }
     }
-#pragma unroll 1
+#pragma unroll kHwUnroll
     for (int rr = 0; rr < mlive_max; ++rr) {
       const bool off = done || rr >= mlive;  // this half has nothing left to do in this round
 #if OC_HW_FAST_ROT
       frot16<LOGLP>(T, S, nT, nS, dT, dS, thr2, off, hmask, again);
 #else
-      rotate16<LOGLP>(T, S, nT, nS, thr2, off, hmask, again);
+      rotate16<LOGLP>(T, S, nT, nS, thr2, off, lostf, again);
 #endif
       if (M > 1) {
 #pragma unroll
@@ -230,12 +230,25 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
         frot16<LOGLP>(S, T, nS, nR, dS, dR, thr2, off || idleB, hmask, again);
         dT = __shfl_sync(FULL, dR, src_up);
 #else
-        rotate16<LOGLP>(S, T, nS, nR, thr2, off || idleB, hmask, again);
+        rotate16<LOGLP>(S, T, nS, nR, thr2, off || idleB, lostf, again);
 #endif
 #pragma unroll
         for (int e = 0; e < 16; ++e) T[e] = shfl2(T[e], src_up);
         nT = __shfl_sync(FULL, nR, src_up);
       }
+#if !OC_HW_FAST_ROT
+      {
+        const unsigned lostmask = __ballot_sync(FULL, lostf);
+        if (lostmask) {  // warp-uniform, rare after the first sweeps
+          const float fT = dot16<LOGLP>(T, T), fS = dot16<LOGLP>(S, S);
+          if (lostmask & hmask) {  // only the half that cancelled takes the refreshed norms
+            nT = fT;
+            nS = fS;
+          }
+          lostf = false;
+        }
+      }
+#endif
     }
     if (!done) ++sweeps;
     const unsigned b = __ballot_sync(FULL, again);
@@ -521,10 +534,13 @@ __device__ __forceinline__ void row_step(bool valid, const Out& io, const float*
   __syncwarp();
 }
 
+#ifndef OC_HW_MINB
+#define OC_HW_MINB 4
+#endif
 constexpr int kHwWarps = 4;  // warps per CTA (8 images)
 
 // ---- head: steps 0..2, image -> Psi_3 (global workspace) ----
-__global__ void __launch_bounds__(kHwWarps * 32, 4) hw_head_kernel(const __grid_constant__ EncodeParams P,
+__global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_head_kernel(const __grid_constant__ EncodeParams P,
                                                                    float* __restrict__ ws_out) {
   extern __shared__ __align__(16) float smem_f[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -564,7 +580,7 @@ __global__ void __launch_bounds__(kHwWarps * 32, 4) hw_head_kernel(const __grid_
 
 // ---- one ROW step from / to the global workspace (N = 3, 4) ----
 template <int N>
-__global__ void __launch_bounds__(kHwWarps * 32, 4) hw_row_kernel(const __grid_constant__ EncodeParams P,
+__global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_row_kernel(const __grid_constant__ EncodeParams P,
                                                                   const float* __restrict__ ws_in,
                                                                   float* __restrict__ ws_out) {
   extern __shared__ __align__(16) float smem_f[];
@@ -578,7 +594,7 @@ __global__ void __launch_bounds__(kHwWarps * 32, 4) hw_row_kernel(const __grid_c
 }
 
 // ---- step 5 (COL): M_5[(s,l), c] = Psi_5[l][s*16 + c], 16 columns of length 64 ----
-__global__ void __launch_bounds__(kHwWarps * 32, 4) hw_col5_kernel(const __grid_constant__ EncodeParams P,
+__global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col5_kernel(const __grid_constant__ EncodeParams P,
                                                                    const float* __restrict__ ws_in,
                                                                    float* __restrict__ ws_out) {
   constexpr int LOGLP = 1;
