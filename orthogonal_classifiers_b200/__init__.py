@@ -27,6 +27,11 @@ from .tools import (  # noqa: F401
 )
 from .variational_mpo_classifiers import (  # noqa: F401
     classifier_predictions,
+    ensemble_predictions,
     evaluate_classifier_top_k_accuracy,
+    evaluate_hard_ensemble_top_k_accuracy,
+    evaluate_soft_ensemble_top_k_accuracy,
     mps_encoding,
+    padded_classifier_predictions,
+    project_classifier,
 )

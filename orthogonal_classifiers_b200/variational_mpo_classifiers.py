@@ -76,10 +76,83 @@ def classifier_predictions(mpo_classifier, mps_test, q_hairy_bitstrings=10):
     ``abs(<image| classifier |bitstring>)``; one batched contraction instead
     of N x n_labels quimb contractions."""
     batch = _batch_of(mps_test)
+    cols = None
+    try:
+        if not (q_hairy_bitstrings is None or isinstance(q_hairy_bitstrings, int)):
+            cols = _label_indices(q_hairy_bitstrings, 0)
+    except ValueError:
+        # general product bitstrings: fix the label legs on the host, one launch per bitstring
+        out = []
+        for b in q_hairy_bitstrings:
+            ov, _ = batched.overlaps_from_mps(batch, project_classifier(mpo_classifier, b), return_argmax=False)
+            out.append(ov.double().cpu().numpy()[:, 0])
+        return [list(row) for row in np.stack(out, axis=1)]
     ov, _ = batched.overlaps_from_mps(batch, mpo_classifier, return_argmax=False)
     ov = ov.double().cpu().numpy()
-    cols = _label_indices(q_hairy_bitstrings, ov.shape[1])
+    if cols is None:
+        cols = _label_indices(q_hairy_bitstrings, ov.shape[1])
     return [list(row) for row in ov[:, cols]]
+
+
+def _classifier_sites(mpo_classifier):
+    if hasattr(mpo_classifier, "data") and not isinstance(mpo_classifier, np.ndarray):
+        return [np.asarray(w) for w in mpo_classifier.data]
+    return [np.asarray(getattr(t, "data", t)) for t in getattr(mpo_classifier, "tensors", mpo_classifier)]
+
+
+def _bitstring_sites(b, sites):
+    """Per-site label-leg vectors of one product bitstring, padded / cut to the
+    label leg of the matching classifier site."""
+    vecs = [np.asarray(getattr(t, "data", t)).reshape(-1) for t in getattr(b, "tensors", b)]
+    if len(vecs) != len(sites):
+        raise ValueError("bitstring and classifier have different numbers of sites")
+    out = []
+    for v, w in zip(vecs, sites):
+        s = w.shape[1]
+        u = np.zeros(s, dtype=np.result_type(v.dtype, np.float64))
+        u[: min(s, v.size)] = v[: min(s, v.size)]
+        out.append(u)
+    return out
+
+
+def project_classifier(mpo_classifier, bitstring):
+    """``mpo_classifier @ b.squeeze()`` (variational_mpo_classifiers.py:313):
+    contract every label leg with the product bitstring.  Host work of
+    O(classifier size); the result has no label leg and is overlapped with
+    the whole image batch by one kernel launch."""
+    sites = _classifier_sites(mpo_classifier)
+    vecs = _bitstring_sites(bitstring, sites)
+    return [np.einsum("dsij,s->dij", w, v)[:, None] for w, v in zip(sites, vecs)]
+
+
+def ensemble_predictions(ensemble, mps_test, q_hairy_bitstrings=10):
+    """variational_mpo_classifiers.py:321-332 — classifier_predictions for each
+    member, every image's label vector normalised to sum 1."""
+    out = []
+    for classifier in ensemble:
+        p = np.asarray(classifier_predictions(classifier, mps_test, q_hairy_bitstrings), dtype=np.float64)
+        out.append([row / np.sum(row) for row in p])
+    return out
+
+
+def padded_classifier_predictions(mpo_classifier, mps_test, padded_q_hairy_bitstrings):
+    """variational_mpo_classifiers.py:334-337 — for every label, the sum over
+    its padding bitstrings of ``abs(<image| classifier |bitstring>)``.
+    ``padded_q_hairy_bitstrings[p][l]`` is the bitstring of padding p, label l
+    (np.sum(..., axis=0) in the reference runs over p).  Each (p, l) fixes all
+    label legs, leaving a label-free MPO that is contracted with the whole
+    batch at once."""
+    batch = _batch_of(mps_test)
+    total = None
+    for paddings in padded_q_hairy_bitstrings:
+        cols = []
+        for b in paddings:
+            proj = project_classifier(mpo_classifier, b)
+            ov, _ = batched.overlaps_from_mps(batch, proj, return_argmax=False)
+            cols.append(ov.double().cpu().numpy()[:, 0])
+        block = np.stack(cols, axis=1)
+        total = block if total is None else total + block
+    return [row for row in total]
 
 
 def evaluate_classifier_top_k_accuracy(predictions, y_test, k):
@@ -87,3 +160,20 @@ def evaluate_classifier_top_k_accuracy(predictions, y_test, k):
     semantics: argpartition top-k, membership, mean)."""
     top_k_predictions = [np.argpartition(np.asarray(p), -k)[-k:] for p in predictions]
     return np.mean([int(i in j) for i, j in zip(y_test, top_k_predictions)])
+
+
+def evaluate_soft_ensemble_top_k_accuracy(e_predictions, y_test, k):
+    """variational_mpo_classifiers.py:348-354 (verbatim semantics)."""
+    top_k_ensemble_predictions = np.sum(e_predictions, axis=0)
+    top_k_predictions = [np.argpartition(p, -k)[-k:] for p in top_k_ensemble_predictions]
+    return np.mean([int(i in j) for i, j in zip(y_test, top_k_predictions)])
+
+
+def evaluate_hard_ensemble_top_k_accuracy(e_predictions, y_test, k):
+    """variational_mpo_classifiers.py:356-363 (verbatim semantics: every member
+    votes with its top-k labels, the k most common win)."""
+    from collections import Counter
+    votes = np.array([[np.argpartition(p, -k)[-k:] for p in member] for member in e_predictions])
+    votes = votes.transpose(1, 0, 2).reshape(len(y_test), -1)
+    winners = [[t[0] for t in Counter(i).most_common(k)] for i in votes]
+    return np.mean([int(i in j) for i, j in zip(y_test, winners)])

@@ -240,3 +240,32 @@ def test_host_pipeline_matches_single_shot(gpu_lib):
         pipe.run(pin, ov, am)
         np.testing.assert_array_equal(ov.numpy().astype(np.float64), ref_ov)
         np.testing.assert_array_equal(am.numpy(), ref_am)
+
+
+def test_ensemble_and_padded_predictions_match_reference(gpu_lib, golden):
+    """variational_mpo_classifiers.py:321-337 on the reference's own outputs
+    (tests/golden/generate_golden_ensemble.py)."""
+    import os
+    ge = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_ensemble.npz"))
+    oc = gpu_lib
+    mps_test = oc.mps_encoding(golden["x_test"], 32)
+    ensemble = [oc.data_to_QTN(golden_sites(golden, f"clf_{n}")) for n in ge["names"]]
+    e = np.array(oc.ensemble_predictions(ensemble, mps_test, 10))
+    ref = ge["e_pred"]
+    assert e.shape == ref.shape
+    assert np.abs(e - ref).max() < 2e-5 * ref.max()
+    for k in (1, 3):
+        assert oc.evaluate_soft_ensemble_top_k_accuracy(e, golden["y_test"], k) == float(ge[f"soft_k{k}"])
+        assert oc.evaluate_hard_ensemble_top_k_accuracy(e, golden["y_test"], k) == float(ge[f"hard_k{k}"])
+    # padded: explicit product bitstrings (second padding scaled by 0.5 on the hairy site)
+    L, c = 10, 5
+    def bits(label, scale):
+        return [np.array([1.0]) if n != c else scale * np.eye(16)[label] for n in range(L)]
+    padded = [[bits(l, 1.0) for l in range(10)], [bits(l, 0.5) for l in range(10)]]
+    p = np.array(oc.padded_classifier_predictions(ensemble[0], mps_test, padded))
+    assert p.shape == ge["padded"].shape
+    assert np.abs(p - ge["padded"]).max() < 2e-5 * ge["padded"].max()
+    # the general-bitstring route of classifier_predictions agrees with the one-hot fast path
+    fast = np.array(oc.classifier_predictions(ensemble[0], mps_test, 10))
+    slow = np.array(oc.classifier_predictions(ensemble[0], mps_test, [bits(l, 0.5) for l in range(10)]))
+    assert np.abs(2 * slow - fast).max() < 2e-5 * fast.max()
