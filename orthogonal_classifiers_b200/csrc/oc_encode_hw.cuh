@@ -28,6 +28,10 @@
 #pragma once
 #include "oc_encode_fast.cuh"
 
+#ifndef OC_HW_LIFT
+#define OC_HW_LIFT 0  // experiment: in-place lifting rotations (measured: no faster, see profiles/encode_r1.md)
+#endif
+
 namespace oc {
 namespace hw {
 
@@ -41,6 +45,16 @@ __device__ __forceinline__ float hsum2(u64 v) {
   unpack2(v, lo, hi);
   return lo + hi;
 }
+// 64-bit shared-memory accesses the compiler must not fuse into 128-bit ones
+// (register pairs of the vector arrays are not quad-aligned: fusing costs MOVs)
+__device__ __forceinline__ void sts64(unsigned addr, u64 v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 lds64(unsigned addr) {
+  u64 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 template <bool G>
@@ -50,13 +64,14 @@ __device__ __forceinline__ float4 ld4(const float* p) {
 }
 
 // dot product of two 32-element register vectors, summed over the LP lanes of a slot
-template <int LOGLP>
+// (NE < 16: only the first NE packed pairs can be non-zero)
+template <int LOGLP, int NE = 16>
 __device__ __forceinline__ float dot16(const u64 (&a)[16], const u64 (&b)[16]) {
   u64 acc[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) acc[e] = mul2(a[e], b[e]);
 #pragma unroll
-  for (int e = 4; e < 16; ++e) acc[e & 3] = fma2(a[e], b[e], acc[e & 3]);
+  for (int e = 4; e < NE; ++e) acc[e & 3] = fma2(a[e], b[e], acc[e & 3]);
   float v = hsum2(add2(add2(acc[0], acc[1]), add2(acc[2], acc[3])));
 #pragma unroll
   for (int o = 0; o < LOGLP; ++o) v += __shfl_xor_sync(FULL, v, 1 << o);
@@ -70,10 +85,10 @@ __device__ __forceinline__ float dot16(const u64 (&a)[16], const u64 (&b)[16]) {
 // ends in round B, and everything a finished / shorter half-warp still has to
 // sit through while its partner image works, so that the result for an image
 // never depends on which image shares its warp.
-template <int LOGLP>
+template <int LOGLP, int NE = 16>
 __device__ __forceinline__ void rotate16(u64 (&a)[16], u64 (&b)[16], float& na, float& nb, float thr2,
                                          bool hold, bool& lostf, bool& again) {
-  const float ab = dot16<LOGLP>(a, b);
+  const float ab = dot16<LOGLP, NE>(a, b);
   const float aa = na, bb = nb;
   const float d = aa * bb;
   const float ab2 = ab * ab;
@@ -100,7 +115,7 @@ __device__ __forceinline__ void rotate16(u64 (&a)[16], u64 (&b)[16], float& na, 
   lostf = lostf || (rot && (n_second < kCancel * aa || n_first < kCancel * bb));
   const u64 c2 = pack2(c, c), s2 = pack2(s, s), ns2 = pack2(ns, ns);
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
+  for (int e = 0; e < NE; ++e) {
     const u64 x = a[e], y = b[e];
     a[e] = fma2(s2, x, mul2(c2, y));
     b[e] = fma2(c2, x, mul2(ns2, y));
@@ -176,7 +191,7 @@ __device__ __forceinline__ void frot16(u64 (&a)[16], u64 (&b)[16], float& na, fl
 #define OC_HW_UNROLL 1
 #endif
 constexpr int kHwUnroll = OC_HW_UNROLL;
-template <int LOGLP>
+template <int LOGLP, int NE = 16>
 __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, float& nS, float thr2,
                                         int lane, int mlive, int mlive_max) {
   constexpr int LP = 1 << LOGLP;
@@ -207,7 +222,7 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
       }
       dT = dS = 1.f;
 #endif
-      const float fT = dot16<LOGLP>(T, T), fS = dot16<LOGLP>(S, S);
+      const float fT = dot16<LOGLP, NE>(T, T), fS = dot16<LOGLP, NE>(S, S);
       if (!done) {
         nT = fT;
         nS = fS;
@@ -219,28 +234,28 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
 #if OC_HW_FAST_ROT
       frot16<LOGLP>(T, S, nT, nS, dT, dS, thr2, off, hmask, again);
 #else
-      rotate16<LOGLP>(T, S, nT, nS, thr2, off, lostf, again);
+      rotate16<LOGLP, NE>(T, S, nT, nS, thr2, off, lostf, again);
 #endif
       if (M > 1) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) T[e] = shfl2(T[e], src_dn);
+        for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_dn);
         float nR = __shfl_sync(FULL, nT, src_dn);
 #if OC_HW_FAST_ROT
         float dR = __shfl_sync(FULL, dT, src_dn);
         frot16<LOGLP>(S, T, nS, nR, dS, dR, thr2, off || idleB, hmask, again);
         dT = __shfl_sync(FULL, dR, src_up);
 #else
-        rotate16<LOGLP>(S, T, nS, nR, thr2, off || idleB, lostf, again);
+        rotate16<LOGLP, NE>(S, T, nS, nR, thr2, off || idleB, lostf, again);
 #endif
 #pragma unroll
-        for (int e = 0; e < 16; ++e) T[e] = shfl2(T[e], src_up);
+        for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_up);
         nT = __shfl_sync(FULL, nR, src_up);
       }
 #if !OC_HW_FAST_ROT
       {
         const unsigned lostmask = __ballot_sync(FULL, lostf);
         if (lostmask) {  // warp-uniform, rare after the first sweeps
-          const float fT = dot16<LOGLP>(T, T), fS = dot16<LOGLP>(S, S);
+          const float fT = dot16<LOGLP, NE>(T, T), fS = dot16<LOGLP, NE>(S, S);
           if (lostmask & hmask) {  // only the half that cancelled takes the refreshed norms
             nT = fT;
             nS = fS;
@@ -265,6 +280,168 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
     }
   }
 #endif
+  return sweeps;
+}
+
+// ---------------------------------------------------------------------------
+// In-place ("lifting") form of the fast rotation.  With x at the first and y at
+// the second position of the pair, t = tan(theta), c = cos(theta):
+//     y <- y + beta x            beta  = t dx / dy          (scale dy <- c dy)
+//     x <- x - alpha y_new       alpha = t c^2 dy / dx      (scale dx <- dx / c)
+// leaves c (y + t x) in y's registers and c (x - t y) in x's, two packed FMAs
+// per element pair, no temporaries and no register renaming; beta = alpha = 0
+// is an exact no-op, so holding a lane costs nothing.  The vectors do NOT swap
+// registers; the position swap of the odd-even ordering is done by the data
+// movement in jacobi16_lift.
+template <int LOGLP>
+__device__ __forceinline__ void lift16(u64 (&x)[16], u64 (&y)[16], float& nx, float& ny, float& dx, float& dy,
+                                       float thr2, bool hold, bool& lostf, bool& again) {
+  const float r_xy = dx * rcp_approx(dy);  // off the critical path
+  const float r_yx = dy * rcp_approx(dx);
+  const float ab = dot16<LOGLP>(x, y) * (dx * dy);
+  const float aa = nx, bb = ny;
+  const float d = aa * bb;
+  const float ab2 = ab * ab;
+  const bool rot = (ab2 > kTol2 * d) && (aa > thr2) && (bb > thr2) && !hold;
+  again = again || (rot && ab2 > kQStop2 * d);
+  const float delta = bb - aa;
+  const float gamma = rot ? ab + ab : 0.f;
+  const float w = sqrt_approx(fmaf(delta, delta, gamma * gamma));
+  const float den = fabsf(delta) + w;
+  const float sg = copysignf(gamma, delta * gamma);
+  const float t = rot ? sg * rcp_approx(den) : 0.f;
+  const float X = fmaf(t, t, 1.f);
+  float c = rsqrt_approx(X);
+  c = c * fmaf(-0.5f * X, c * c, 1.5f);  // Newton: the transformation is orthogonal to ~1 ulp for the t used
+  const float beta = rot ? t * r_xy : 0.f;
+  const float alpha = rot ? t * r_yx * (c * c) : 0.f;
+  const u64 b2 = pack2(beta, beta), na2 = pack2(-alpha, -alpha);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) y[e] = fma2(b2, x[e], y[e]);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) x[e] = fma2(na2, y[e], x[e]);
+  const float n_y = fmaf(t, ab, bb), n_x = fmaf(-t, ab, aa);  // t = 0: unchanged
+  lostf = lostf || (rot && (n_x < kCancel * aa || n_y < kCancel * bb));
+  nx = n_x;
+  ny = n_y;
+  dy = rot ? c * dy : dy;
+  dx = rot ? dx * (X * c) : dx;
+}
+
+// Odd-even ordering with the lifting rotation.  Register sets P, Q of slot k
+// hold line positions (2k, 2k+1) between iterations.  One iteration:
+//   A: rotate (P_k, Q_k)                    -> logically P = second, Q = first
+//   Q moves one slot down (lane k gets first_{k+1})
+//   B: rotate (P_k, Q_k) = (second_k, first_{k+1})
+//   P moves one slot up (lane k+1 gets its new first position)
+// The two vectors that sit out round B (first_0 and second_{m-1}) change sets at
+// the line ends through a per-lane scratch row in shared memory (written and
+// read by the same lane).  A half that is finished, or past its own line length
+// in this sweep, neither rotates nor moves (shuffle source = itself), so its
+// state never depends on the image sharing its warp.
+// refl: refl_floats(LOGLP) floats of shared memory of this IMAGE (each lane uses its own rows).
+template <int LOGLP>
+__device__ __forceinline__ int jacobi16_lift(u64 (&P)[16], u64 (&Q)[16], float& nP, float& nQ, float thr2,
+                                             int lane, int mlive, int mlive_max, float* refl) {
+  constexpr int LP = 1 << LOGLP;
+  constexpr int M = 16 >> LOGLP;
+  const int l16 = lane & 15, hb = lane & 16;
+  const int slot = l16 >> LOGLP;
+  const int src_dn = hb | ((l16 + LP) & 15);
+  const int src_up = hb | ((l16 - LP) & 15);
+  const bool live = slot < mlive;
+  const bool first = live && slot == 0, last = live && slot == mlive - 1;
+  const bool idleB = slot >= mlive - 1;
+  const unsigned hmask = 0xffffu << hb;
+  int sweeps = 0;
+  bool done = mlive == 0;
+  float dP = 1.f, dQ = 1.f;
+  const unsigned rq = (unsigned)__cvta_generic_to_shared(refl + (l16 & (LP - 1)) * 32);
+  const unsigned rp = (unsigned)__cvta_generic_to_shared(refl + (LP + (l16 & (LP - 1))) * 32);
+#pragma unroll 1
+  for (int sw = 0; sw < kMaxSweeps; ++sw) {
+    bool again = false;
+    bool lostf = false;
+    {
+      // fold the scale factors back into the data, refresh the norms
+      const u64 p2 = pack2(dP, dP), q2 = pack2(dQ, dQ);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        P[e] = mul2(P[e], p2);
+        Q[e] = mul2(Q[e], q2);
+      }
+      dP = dQ = 1.f;
+      const float fP = dot16<LOGLP>(P, P), fQ = dot16<LOGLP>(Q, Q);
+      if (!done && live) {
+        nP = fP;
+        nQ = fQ;
+      }
+    }
+#pragma unroll 1
+    for (int rr = 0; rr < mlive_max; ++rr) {
+      const bool off = done || rr >= mlive;  // this half sits this round pair out
+      lift16<LOGLP>(P, Q, nP, nQ, dP, dQ, thr2, off || !live, lostf, again);
+      if (M > 1) {
+        const bool mvf = first && !off, mvl = last && !off;
+        const int sq = off ? lane : src_dn, sp = off ? lane : src_up;
+        const float keepN = nQ, keepD = dQ;
+        if (mvf) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sts64(rq + 8 * e, Q[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) Q[e] = shfl2(Q[e], sq);
+        nQ = __shfl_sync(FULL, nQ, sq);
+        dQ = __shfl_sync(FULL, dQ, sq);
+        lift16<LOGLP>(P, Q, nP, nQ, dP, dQ, thr2, off || idleB, lostf, again);
+        const float keepN2 = nP, keepD2 = dP;
+        if (mvl) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sts64(rp + 8 * e, P[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) P[e] = shfl2(P[e], sp);
+        nP = __shfl_sync(FULL, nP, sp);
+        dP = __shfl_sync(FULL, dP, sp);
+        if (mvf) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) P[e] = lds64(rq + 8 * e);
+          nP = keepN;
+          dP = keepD;
+        }
+        if (mvl) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) Q[e] = lds64(rp + 8 * e);
+          nQ = keepN2;
+          dQ = keepD2;
+        }
+      }
+      {
+        const unsigned lostmask = __ballot_sync(FULL, lostf);
+        if (lostmask) {  // warp-uniform, rare after the first sweeps
+          const float fP = dot16<LOGLP>(P, P) * dP * dP, fQ = dot16<LOGLP>(Q, Q) * dQ * dQ;
+          if ((lostmask & hmask) && live && !off) {  // only the half that cancelled takes the refreshed norms
+            nP = fP;
+            nQ = fQ;
+          }
+          lostf = false;
+        }
+      }
+    }
+    if (!done) ++sweeps;
+    const unsigned b = __ballot_sync(FULL, again);
+    if (M == 1 || mlive <= 1 || !(b & hmask)) done = true;
+    if (__all_sync(FULL, done)) break;
+  }
+  {
+    // dead slots may have collected copies of the end vectors: clear them
+    const u64 p2 = live ? pack2(dP, dP) : 0ull, q2 = live ? pack2(dQ, dQ) : 0ull;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      P[e] = live ? mul2(P[e], p2) : 0ull;
+      Q[e] = live ? mul2(Q[e], q2) : 0ull;
+    }
+  }
   return sweeps;
 }
 
@@ -376,6 +553,8 @@ __device__ __forceinline__ Out make_out(const EncodeParams& P, int64_t img, int 
   return o;
 }
 
+// floats of shared memory one image needs for the end-of-line scratch of jacobi16_lift
+__host__ __device__ constexpr int refl_floats(int loglp) { return OC_HW_LIFT ? (64 << loglp) : 0; }
 // floats of shared memory one image needs for the U columns of ROW step n
 __host__ __device__ constexpr int ysm_floats(int n) { return (2 << n) * ((2 << n) + 2); }
 
@@ -385,7 +564,7 @@ __host__ __device__ constexpr int ysm_floats(int n) { return (2 << n) * ((2 << n
 // ysm: ysm_floats(N) floats of shared memory for this image.
 template <int N, bool GSRC, bool GDST>
 __device__ __forceinline__ void row_step(bool valid, const Out& io, const float* psi_in, float* psi_out,
-                                         float* ysm, int lane) {
+                                         float* ysm, float* refl, int lane) {
   constexpr int B = 1 << N, Q = 1 << (9 - N);
   constexpr int LOGLP = 4 - N, LP = 1 << LOGLP;
   constexpr int YSTR = 2 * B + 2;
@@ -417,7 +596,11 @@ __device__ __forceinline__ void row_step(bool valid, const Out& io, const float*
   const int mlive_max = ml0 > ml1 ? ml0 : ml1;
   int sweeps = 0;
   if (mlive_max > 0) {
+#if OC_HW_LIFT
+    sweeps = jacobi16_lift<LOGLP>(T, S, nT, nS, thr2, lane, mlive, mlive_max, refl);
+#else
     sweeps = jacobi16<LOGLP>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+#endif
     nT = dot16<LOGLP>(T, T);
     nS = dot16<LOGLP>(S, S);
   }
@@ -549,6 +732,7 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_head_kernel(cons
   const bool valid = img < P.N;
   float* buf = smem_f + (size_t)(warp * 2 + h) * 1024;
   float* ysm = smem_f + (size_t)kHwWarps * 2 * 1024 + (size_t)(warp * 2 + h) * ysm_floats(2);
+  float* refl = smem_f + (size_t)kHwWarps * 2 * (1024 + ysm_floats(2)) + (size_t)(warp * 2 + h) * refl_floats(3);
   // stage the tail-padded image (tools.py:218-220: flat padding, pixel i -> amplitude i)
   {
     const char* src = reinterpret_cast<const char*>(P.images);
@@ -573,9 +757,9 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_head_kernel(cons
   }
   __syncwarp();
   const int64_t im = valid ? img : 0;
-  row_step<0, false, false>(valid, make_out(P, im, 0), buf, buf, ysm, lane);
-  row_step<1, false, false>(valid, make_out(P, im, 1), buf, buf, ysm, lane);
-  row_step<2, false, true>(valid, make_out(P, im, 2), buf, ws_out + (size_t)im * kWsStride, ysm, lane);
+  row_step<0, false, false>(valid, make_out(P, im, 0), buf, buf, ysm, refl, lane);
+  row_step<1, false, false>(valid, make_out(P, im, 1), buf, buf, ysm, refl, lane);
+  row_step<2, false, true>(valid, make_out(P, im, 2), buf, ws_out + (size_t)im * kWsStride, ysm, refl, lane);
 }
 
 // ---- one ROW step from / to the global workspace (N = 3, 4) ----
@@ -590,7 +774,9 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_row_kernel(const
   const bool valid = img < P.N;
   const int64_t im = valid ? img : 0;
   row_step<N, true, true>(valid, make_out(P, im, N), ws_in + (size_t)im * kWsStride,
-                          ws_out + (size_t)im * kWsStride, smem_f + (size_t)(warp * 2 + h) * ysm_floats(N), lane);
+                          ws_out + (size_t)im * kWsStride, smem_f + (size_t)(warp * 2 + h) * ysm_floats(N),
+                          smem_f + (size_t)kHwWarps * 2 * ysm_floats(N) + (size_t)(warp * 2 + h) * refl_floats(4 - N),
+                          lane);
 }
 
 // ---- step 5 (COL): M_5[(s,l), c] = Psi_5[l][s*16 + c], 16 columns of length 64 ----
@@ -598,8 +784,10 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col5_kernel(cons
                                                                    const float* __restrict__ ws_in,
                                                                    float* __restrict__ ws_out) {
   constexpr int LOGLP = 1;
+  extern __shared__ __align__(16) float smem_f[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l16 = lane & 15, h = lane >> 4;
+  float* refl = smem_f + (size_t)(warp * 2 + h) * refl_floats(LOGLP);
   const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
   const bool valid = img < P.N;
   const int64_t im = valid ? img : 0;
@@ -628,7 +816,19 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col5_kernel(cons
   const int mlive_max = fmask ? 8 : 0;
   int sweeps = 0;
   if (mlive_max > 0) {
-    sweeps = jacobi16<LOGLP>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+#if OC_HW_LIFT
+    sweeps = jacobi16_lift<LOGLP>(T, S, nT, nS, thr2, lane, mlive, mlive_max, refl);
+#else
+    // rows l >= rank(bond 5) of Psi_5 are zero (<= 24 for 784 pixels): when the
+    // last 4 packed pairs (l >= 24) are zero in the whole warp, skip them
+    bool tailnz = false;
+#pragma unroll
+    for (int j = 12; j < 16; ++j) tailnz = tailnz || (T[j] | S[j]) != 0ull;
+    if (__any_sync(FULL, tailnz))
+      sweeps = jacobi16<LOGLP>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+    else
+      sweeps = jacobi16<LOGLP, 12>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+#endif
     nT = dot16<LOGLP>(T, T);
     nS = dot16<LOGLP>(S, S);
   }
@@ -731,13 +931,14 @@ inline bool supported(const EncodeParams& P) { return P.L == 10 && P.D > 16; }
 inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, int sms, cudaStream_t st) {
   const int per_cta = kHwWarps * 2;
   const int grid = (int)((P.N + per_cta - 1) / per_cta);
-  const size_t smem_head = (size_t)per_cta * (1024 + ysm_floats(2)) * sizeof(float);
-  const size_t smem3 = (size_t)per_cta * ysm_floats(3) * sizeof(float);
-  const size_t smem4 = (size_t)per_cta * ysm_floats(4) * sizeof(float);
+  const size_t smem_head = (size_t)per_cta * (1024 + ysm_floats(2) + refl_floats(3)) * sizeof(float);
+  const size_t smem3 = (size_t)per_cta * (ysm_floats(3) + refl_floats(1)) * sizeof(float);
+  const size_t smem4 = (size_t)per_cta * (ysm_floats(4) + refl_floats(0)) * sizeof(float);
+  const size_t smem5 = (size_t)per_cta * refl_floats(1) * sizeof(float);
   hw_head_kernel<<<grid, kHwWarps * 32, smem_head, st>>>(P, ws0);
   hw_row_kernel<3><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1);
   hw_row_kernel<4><<<grid, kHwWarps * 32, smem4, st>>>(P, ws1, ws0);
-  hw_col5_kernel<<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
+  hw_col5_kernel<<<grid, kHwWarps * 32, smem5, st>>>(P, ws0, ws1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return launch_steps<32, 6, 10>(P, ws1, nullptr, sms, st);
