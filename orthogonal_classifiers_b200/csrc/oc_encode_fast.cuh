@@ -29,7 +29,10 @@ namespace oc {
 typedef unsigned long long u64;
 
 constexpr float kTol2 = 1e-12f;    // rotate if (a.b)^2 > (1e-6)^2 |a|^2 |b|^2
-constexpr float kQStop2 = 1e-7f;   // a sweep whose largest rotation had cos^2 below this is the last
+#ifndef OC_QSTOP2
+#define OC_QSTOP2 1e-7f
+#endif
+constexpr float kQStop2 = OC_QSTOP2;  // a sweep whose largest rotation had cos^2 below this is the last
 constexpr float kFloor2 = 1e-12f;  // vectors below 1e-6 ||M||_F are numerically zero
 constexpr float kCancel = 0.05f;   // norm update lost > 95 %: recompute it from the data
 constexpr int kMaxSweeps = 14;

@@ -78,8 +78,11 @@ __device__ __forceinline__ void mm_kmajor(float* __restrict__ C, int ldc, const 
                                           int ldx, const float* __restrict__ Y, int ldy, int M, int N,
                                           int K, int lane) {
   const int tm = (M + 3) >> 2, tn = (N + 3) >> 2, nt = tm * tn;
+  // tm is a power of two for the natural bond profiles: shift instead of divide
+  const bool p2 = (tm & (tm - 1)) == 0;
+  const int sh = 31 - __clz(tm);
   for (int t = lane; t < nt; t += 32) {
-    const int tj = t / tm, ti = t - tj * tm;
+    const int tj = p2 ? (t >> sh) : t / tm, ti = t - tj * tm;
     const float* xp = Xt + 4 * ti;
     const float* yp = Y + 4 * tj;
     float acc[4][4];
@@ -111,6 +114,56 @@ __device__ __forceinline__ void mm_kmajor(float* __restrict__ C, int ldc, const 
         for (int j = 0; j < 4; ++j)
           if (m0 + i < M && n0 + j < N) C[(m0 + i) * ldc + n0 + j] = acc[i][j];
     }
+  }
+}
+
+// The large contractions of the chain (M * N * nslice == 1024 outputs, e.g. the
+// two s-slices of a 16 x 32 or one 32 x 32): exactly one 8 x 4 register tile
+// per lane, 3 LDS.128 per 32 FMA, no tile loop.  Slice s uses C + s*offC,
+// Xt + s*offX, Y + s*offY.  M % 8 == 0, N % 4 == 0, tiles per slice a power of two.
+__device__ __forceinline__ void mm_kmajor_84(float* __restrict__ C, int ldc, int offC,
+                                             const float* __restrict__ Xt, int ldx, int offX,
+                                             const float* __restrict__ Y, int ldy, int offY, int M, int N,
+                                             int K, int lane) {
+  const int tm = M >> 3, tn = N >> 2;
+  const int per = tm * tn;                  // tiles per slice (16 or 32)
+  const int s = lane >> (31 - __clz(per)), t = lane & (per - 1);
+  const int shm = 31 - __clz(tm);
+  const int tj = t >> shm, ti = t - (tj << shm);
+  const float* xp = Xt + s * offX + 8 * ti;
+  const float* yp = Y + s * offY + 4 * tj;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 x0 = *reinterpret_cast<const float4*>(xp + k * ldx);
+    const float4 x1 = *reinterpret_cast<const float4*>(xp + k * ldx + 4);
+    const float4 y = *reinterpret_cast<const float4*>(yp + k * ldy);
+    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    const float yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+  }
+  float* cp = C + s * offC + (8 * ti) * ldc + 4 * tj;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(cp + i * ldc) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+}
+
+// nslice contractions of the same shape; picks the 8x4 single-tile form when it applies
+__device__ __forceinline__ void mm_slices(float* __restrict__ C, int ldc, int offC, const float* __restrict__ Xt,
+                                          int ldx, int offX, const float* __restrict__ Y, int ldy, int offY,
+                                          int M, int N, int K, int nslice, int lane) {
+  if (M * N * nslice == 1024 && (M & 7) == 0 && (N & 3) == 0) {
+    mm_kmajor_84(C, ldc, offC, Xt, ldx, offX, Y, ldy, offY, M, N, K, lane);
+  } else {
+    for (int s = 0; s < nslice; ++s)
+      mm_kmajor(C + s * offC, ldc, Xt + s * offX, ldx, Y + s * offY, ldy, M, N, K, lane);
   }
 }
 
@@ -227,15 +280,14 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       const float* W = sW + F.w_off[n];
       const float* A = As + F.a_off[n];
       // T[(s,a)][B'] = sum_B Et[B][a] W[s][B][B']
-      for (int s = 0; s < 2; ++s)
-        mm_kmajor(Tb + s * al * ldT, ldT, E, ldE, W + s * Bl * ldW, ldW, al, Br, Bl, lane);
+      mm_slices(Tb, ldT, al * ldT, E, ldE, 0, W, ldW, Bl * ldW, al, Br, Bl, 2, lane);
       __syncwarp();
       if (n + 1 < c) {
         // Et'[B'][a'] = sum_(s,a) T[(s,a)][B'] A[(s,a)][a']
-        mm_kmajor(E, ldA, Tb, ldT, A, ldA, Br, ar, 2 * al, lane);
+        mm_slices(E, ldA, 0, Tb, ldT, 0, A, ldA, 0, Br, ar, 2 * al, 1, lane);
       } else {
         // EL[a'][B'] = sum_(s,a) A[(s,a)][a'] T[(s,a)][B']
-        mm_kmajor(E, ldT, A, ldA, Tb, ldT, ar, Br, 2 * al, lane);
+        mm_slices(E, ldT, 0, A, ldA, 0, Tb, ldT, 0, ar, Br, 2 * al, 1, lane);
       }
       __syncwarp();
     }
@@ -252,8 +304,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       const float* Wt = sW + F.w_off[n];  // [s][B'][B]
       const float* At = As + F.a_off[n];  // [s][a'][a]
       // T'[s][B'][a] = sum_a' R[a'][B'] At[s][a'][a]
-      for (int s = 0; s < 2; ++s)
-        mm_kmajor(Tb + s * Br * ldTp, ldTp, R, ldR, At + s * ar * ldAt, ldAt, Br, al, ar, lane);
+      mm_slices(Tb, ldTp, Br * ldTp, R, ldR, 0, At, ldAt, ar * ldAt, Br, al, ar, 2, lane);
       __syncwarp();
       // R'[a][B] = sum_(s,B') T'[(s,B')][a] Wt[(s,B')][B]
       mm_kmajor(R2, ldWt, Tb, ldTp, Wt, ldWt, al, Bl, 2 * Br, lane);
@@ -269,10 +320,10 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       float* G = Tb;                      // [s][a][B']  (2 * al * ldG <= 1024)
       float* H = Tb + 1024;               // [s][B][B']  (2 * Bl * ldH <= 1024)
       // G[s][a][B'] = sum_a' At[s][a'][a] ER[a'][B']
-      for (int s = 0; s < 2; ++s) mm_kmajor(G + s * al * ldG, ldG, At + s * ar * ldAt, ldAt, R, ldR, al, Br, ar, lane);
+      mm_slices(G, ldG, al * ldG, At, ldAt, ar * ldAt, R, ldR, 0, al, Br, ar, 2, lane);
       __syncwarp();
       // H[s][B][B'] = sum_a EL[a][B] G[s][a][B']
-      for (int s = 0; s < 2; ++s) mm_kmajor(H + s * Bl * ldH, ldH, E, ldEL, G + s * al * ldG, ldG, Bl, Br, al, lane);
+      mm_slices(H, ldH, Bl * ldH, E, ldEL, 0, G, ldG, al * ldG, Bl, Br, al, 2, lane);
       __syncwarp();
       // out[l] = sum_(s,B,B') Wc[(s,B,B')][l] H[s][B][B']; lane = (label quad, part)
       const int lq_n = F.Spad >> 2;  // label quads (power of two <= 8)
