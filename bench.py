@@ -27,7 +27,12 @@ D_ENCODE = 32
 D_TOTAL = 32
 BATCH = 70_000
 FLOP_ENCODE = 1_210_241      # SURVEY.md §8(d), algorithmic, per image
+FLOP_STEP4 = 721_920         # the 32 x 32 SVD step (bond 4 -> 5), the dominant kernel
 FLOP_CLASSIFY = 257_456
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
+# (hw_row_kernel<4>, 70,000 images) from `ncu --set full` of this command
+# (profiles/README.md); None until a capture of the current kernel exists
+TRAFFIC_STEP4_BYTES = None
 BYTES_IMG = 784 * 4 + 16 * 4 + 4
 
 
@@ -206,6 +211,8 @@ def main():
     if sampler:
         sampler.start()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # per-launch CUDA events inside the library, on the launching stream, over the timed steps
+    check(lib.oc_set_option(b"enc_events", 1))
     barrier()
     t_start.record(stream)
     for k in range(args.steps):
@@ -214,6 +221,11 @@ def main():
     barrier()
     ms = t_start.elapsed_time(t_end)
     correct = counts.clone()
+    import ctypes as C
+    launch_ms = (C.c_float * 5)()
+    check(lib.oc_encode_step_ms(launch_ms, 5))   # mean over the (last <= 16) timed steps
+    check(lib.oc_set_option(b"enc_events", 0))
+    launch_ms = [float(v) for v in launch_ms]
 
     # ---- end to end through the public API: pinned host in, host out -------
     imgs_pin = torch.from_numpy(imgs_h).pin_memory()
@@ -237,19 +249,33 @@ def main():
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+
+    # same, with the pixels as the uint8 MNIST ships (the synthetic images are k/255 exactly);
+    # /255 happens in the encoder's load (OC_U8)
+    imgs_u8 = torch.from_numpy(np.rint(imgs_h * 255.0).astype(np.uint8)).pin_memory()
+    pipe8 = batched.HostPipeline(clf, 784, D_ENCODE, chunk=17_500, in_dtype=torch.uint8)
+    for _ in range(2):
+        pipe8.run(imgs_u8, ov_pin, am_pin)
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record(stream)
+    for _ in range(args.steps):
+        pipe8.run(imgs_u8, ov_pin, am_pin)
+    u1.record(stream)
+    barrier()
+    e2e_u8_ms = u0.elapsed_time(u1)
     clocks = sampler.stop() if sampler else None
 
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms, e2e_u8_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = t.tolist()
+    ms, e2e_ms, e2e_u8_ms = t.tolist()
 
     if rank == 0:
         enc_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
         ovl_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
         # fp32 FMA peak measured here (MEASURED_PEAKS.json has no fp32 figure)
         sink = torch.zeros(1, dtype=torch.float32, device=dev)
-        import ctypes as C
         flops = C.c_double()
         best = 0.0
         for it in range(4):
@@ -267,6 +293,7 @@ def main():
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
         enc_tflops = FLOP_ENCODE * N / (enc_ms * 1e-3) / 1e12
+        step4_tflops = FLOP_STEP4 * N / (launch_ms[2] * 1e-3) / 1e12 if launch_ms[2] > 0 else None
         value = world * N * args.steps / (ms * 1e-3)
         e2e_value = world * N * args.steps / (e2e_ms * 1e-3)
         line = {
@@ -280,15 +307,30 @@ def main():
                        "parallelism": f"dp{world} (images sharded, classifier replicated)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(N * 784 * 4),
-                    "d2h_bytes_per_step": int(N * (16 * 4 + 4))},
-            # per step: 5 encode kernels per 131,072-image chunk + overlap prep + overlap + count
+                    "d2h_bytes_per_step": int(N * (16 * 4 + 4)), "host_input": "float32 pixels, pinned"},
+            "e2e_u8": {"value": world * N * args.steps / (e2e_u8_ms * 1e-3), "unit": "images/s",
+                       "h2d_bytes_per_step": int(N * 784), "d2h_bytes_per_step": int(N * (16 * 4 + 4)),
+                       "host_input": "uint8 pixels (MNIST's native type), pinned; /255 in the encoder load"},
+            # per step: 5 encode kernels (head | step 3 | step 4 | step 5 | tail) per 131,072-image
+            # chunk + overlap prep + overlap + count
             "gpu_launches": (5 * ((N + 131071) // 131072) + 3) * args.steps,
-            "kernels_ms": {"encode": enc_ms, "overlap": ovl_ms},
-            "roofline": {"bound": "fp32_fma", "kernel": "encode", "achieved": enc_tflops, "peak": best,
-                         "unit": "TFLOP/s", "frac": enc_tflops / best if best else None, "traffic": None,
+            "kernels_ms": {"encode": enc_ms, "overlap": ovl_ms,
+                           "encode_launches": dict(zip(["head_0_2", "step3", "step4", "step5", "tail_6_9"],
+                                                       launch_ms))},
+            # dominant kernel: hw_row_kernel<4> (the 32 x 32 SVD step), timed with CUDA events on the
+            # launching stream inside the timed region (oc_encode_step_ms)
+            "roofline": {"bound": "fp32_fma", "kernel": "hw_row_kernel<4> (encode step 4, 32x32 SVD)",
+                         "achieved": step4_tflops, "peak": best, "unit": "TFLOP/s",
+                         "frac": step4_tflops / best if best else None,
+                         "traffic": TRAFFIC_STEP4_BYTES,
+                         "algorithmic_flop_per_image": FLOP_STEP4,
+                         "ms_per_launch": launch_ms[2],
                          "peak_source": "fp32 FMA microbenchmark (oc_fma_peak_launch) in this run; "
-                                        "MEASURED_PEAKS.json has no fp32 figure; nominal 74.4",
-                         "algorithmic_flop_per_image": FLOP_ENCODE,
+                                        "MEASURED_PEAKS.json has no fp32 figure (hbm_gbs / bf16 only); nominal 74.4",
+                         "why_not_hbm_or_tensor": "458 FLOP/B (HBM bound would be 2.0 G img/s) and no GEMM-shaped "
+                                                  "work: one-sided Jacobi on 32-vectors (DESIGN.md §4)",
+                         "encode": {"achieved": enc_tflops, "frac": enc_tflops / best if best else None,
+                                    "algorithmic_flop_per_image": FLOP_ENCODE},
                          "path_frac": (FLOP_ENCODE + FLOP_CLASSIFY) * N * args.steps / (ms * 1e-3) / 1e12 / best
                          if best else None,
                          "hbm_frac": BYTES_IMG * N * args.steps / (ms * 1e-3) / 1e9 / hbm},

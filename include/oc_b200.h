@@ -145,6 +145,17 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N,
                      const int32_t* clf_s_host, void* overlaps_out_host,
                      int32_t* argmax_out_host, void* stream);
 
+/* Diagnostics: per-launch device times of the encoder.  After
+ * oc_set_option("enc_events", 1) every oc_encode_batch records a CUDA event on
+ * its stream before and after each kernel of the step-major chain (head |
+ * step 3 | step 4 | step 5 | tail; first chunk of the call only), keeping the
+ * last 16 calls.  oc_encode_step_ms synchronises on those events and returns
+ * the elapsed milliseconds of the `n` launches (n <= 5) averaged over the
+ * recorded calls; used by bench.py for the roofline of the dominant kernel
+ * (step 4).  Setting the option (to 0 or 1) forgets earlier records.  Returns
+ * OC_E_ARG when nothing was recorded. */
+int oc_encode_step_ms(float* ms_out_host, int n);
+
 /* Diagnostics: peak-FMA microbenchmark kernel used by bench.py to measure the
  * fp32 FMA roofline denominator on the device it runs on.  Launches one
  * kernel of `iters` dependent-free FMA chains; returns flops executed.

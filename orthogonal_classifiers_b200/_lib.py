@@ -15,7 +15,7 @@ OC_MAX_SITES = 64
 EXPORTS = [
     "oc_version", "oc_last_error", "oc_set_option", "oc_mps_layout", "oc_svals_width",
     "oc_encode_batch", "oc_overlap_batch", "oc_encode_classify", "oc_count_correct",
-    "oc_pack_classifier", "oc_classify_host", "oc_fma_peak_launch",
+    "oc_pack_classifier", "oc_classify_host", "oc_fma_peak_launch", "oc_encode_step_ms",
 ]
 
 
@@ -47,6 +47,7 @@ def _load():
     lib.oc_classify_host.argtypes = [vp, i32, i64, i32, i64, i32, i32, i32, i32, vp, i64, p32, p32,
                                      vp, vp, vp]
     lib.oc_fma_peak_launch.argtypes = [i64, vp, C.POINTER(C.c_double), vp]
+    lib.oc_encode_step_ms.argtypes = [C.POINTER(C.c_float), C.c_int]
     for name in EXPORTS:
         if name not in ("oc_last_error",):
             getattr(lib, name).restype = i32

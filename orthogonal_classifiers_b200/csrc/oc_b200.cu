@@ -97,6 +97,11 @@ int oc_set_option(const char* key, int value) {
     g_force_generic = value;
     return OC_OK;
   }
+  if (key && !strcmp(key, "enc_events")) {
+    oc::encode_events().on = value != 0;
+    oc::encode_events().ncalls = 0;
+    return OC_OK;
+  }
   if (key && !strcmp(key, "enc_hw")) {
     oc::encode_use_hw() = value;
     return OC_OK;
@@ -436,6 +441,24 @@ __global__ void __launch_bounds__(256) fma2_peak_kernel(int64_t iters, float* si
   if (r == 123.456f) sink[0] = r;
 }
 }  // namespace
+
+int oc_encode_step_ms(float* ms_out_host, int n) {
+  oc::EncodeEvents& ee = oc::encode_events();
+  if (!ms_out_host || n < 1 || n > 5) return fail(OC_E_ARG, "n=%d outside [1,5]", n);
+  const int calls = std::min(ee.ncalls, oc::kEvRing);
+  if (calls < 1) return fail(OC_E_ARG, "no encoder events recorded (oc_set_option(\"enc_events\", 1) first)");
+  for (int i = 0; i < n; ++i) ms_out_host[i] = 0.f;
+  for (int c = 0; c < calls; ++c) {
+    cudaEvent_t* ev = ee.ev[(ee.ncalls - 1 - c) % oc::kEvRing];
+    OC_CUDA(cudaEventSynchronize(ev[5]));
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      OC_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      ms_out_host[i] += ms / calls;
+    }
+  }
+  return OC_OK;
+}
 
 int oc_fma_peak_launch(int64_t iters, float* sink_dev, double* flops_out, void* stream) {
   const int threads = 256;

@@ -533,6 +533,27 @@ __global__ void __launch_bounds__(128, 6) encode_steps_kernel(const __grid_const
   }
 }
 
+// optional per-launch CUDA events (oc_set_option("enc_events", 1)): a ring of
+// the last kEvRing oc_encode_batch calls, 6 events each (before / after the five
+// launches of the first chunk), recorded on the launching stream
+constexpr int kEvRing = 16;
+struct EncodeEvents {
+  bool on = false;
+  int ncalls = 0;
+  cudaEvent_t ev[kEvRing][6] = {};
+  void mark(int i, cudaStream_t st) {
+    if (!on) return;
+    cudaEvent_t& e = ev[ncalls % kEvRing][i];
+    if (!e) cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    if (i == 5) ++ncalls;
+  }
+};
+inline EncodeEvents& encode_events() {
+  static EncodeEvents e;
+  return e;
+}
+
 inline bool encode_fast_supported(const EncodeParams& P) { return P.L == 10; }
 
 inline int& encode_warps_per_cta() {
@@ -561,11 +582,19 @@ inline cudaError_t launch_steps(const EncodeParams& P, const float* ws_in, float
 template <int DPAD>
 inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, int sms, cudaStream_t st) {
   cudaError_t e;
+  EncodeEvents& ee = encode_events();
+  ee.mark(0, st);
   if ((e = launch_steps<DPAD, 0, 3>(P, nullptr, ws0, sms, st)) != cudaSuccess) return e;
+  ee.mark(1, st);
   if ((e = launch_steps<DPAD, 3, 4>(P, ws0, ws1, sms, st)) != cudaSuccess) return e;
+  ee.mark(2, st);
   if ((e = launch_steps<DPAD, 4, 5>(P, ws1, ws0, sms, st)) != cudaSuccess) return e;
+  ee.mark(3, st);
   if ((e = launch_steps<DPAD, 5, 6>(P, ws0, ws1, sms, st)) != cudaSuccess) return e;
-  return launch_steps<DPAD, 6, 10>(P, ws1, nullptr, sms, st);
+  ee.mark(4, st);
+  e = launch_steps<DPAD, 6, 10>(P, ws1, nullptr, sms, st);
+  ee.mark(5, st);
+  return e;
 }
 
 constexpr int64_t kEncodeChunk = 131072;  // images per pass: 2 x 512 MB of Psi workspace
@@ -597,6 +626,12 @@ inline int encode_fast_launch(const EncodeParams& P0, float* ws, int sms, cudaSt
     float* ws0 = ws;
     float* ws1 = ws + (size_t)chunk * kWsStride;
     cudaError_t e;
+    const bool ev_on = encode_events().on;
+    if (lo > 0) encode_events().on = false;  // events cover the first chunk of the call
+    struct Restore {
+      bool v;
+      ~Restore() { encode_events().on = v; }
+    } restore{ev_on};
     if (encode_use_hw() && hw::supported(P)) {
       e = hw::launch_chain(P, ws0, ws1, sms, st);
       if (e != cudaSuccess) return (int)e;

@@ -739,12 +739,16 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_head_kernel(cons
     const int esz = P.in_dtype == 0 ? 4 : (P.in_dtype == 1 ? 8 : 1);
     const void* rowp = src + (size_t)(valid ? img : 0) * P.ld * esz;
     const bool vec = P.in_dtype == 0 && ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const bool vec8 = P.in_dtype == 2 && ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
 #pragma unroll 4
     for (int i = 4 * l16; i < 1024; i += 64) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) {
         if (vec && i + 3 < P.n_pix) {
           v = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rowp) + i));
+        } else if (vec8 && i + 3 < P.n_pix) {
+          const uchar4 u = __ldcs(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(rowp) + i));
+          v = make_float4(float(u.x) / 255.f, float(u.y) / 255.f, float(u.z) / 255.f, float(u.w) / 255.f);
         } else {
           if (i < P.n_pix) v.x = load_pixel<float>(rowp, P.in_dtype, i);
           if (i + 1 < P.n_pix) v.y = load_pixel<float>(rowp, P.in_dtype, i + 1);
@@ -935,13 +939,21 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, i
   const size_t smem3 = (size_t)per_cta * (ysm_floats(3) + refl_floats(1)) * sizeof(float);
   const size_t smem4 = (size_t)per_cta * (ysm_floats(4) + refl_floats(0)) * sizeof(float);
   const size_t smem5 = (size_t)per_cta * refl_floats(1) * sizeof(float);
+  EncodeEvents& ee = encode_events();
+  ee.mark(0, st);
   hw_head_kernel<<<grid, kHwWarps * 32, smem_head, st>>>(P, ws0);
+  ee.mark(1, st);
   hw_row_kernel<3><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1);
+  ee.mark(2, st);
   hw_row_kernel<4><<<grid, kHwWarps * 32, smem4, st>>>(P, ws1, ws0);
+  ee.mark(3, st);
   hw_col5_kernel<<<grid, kHwWarps * 32, smem5, st>>>(P, ws0, ws1);
+  ee.mark(4, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  return launch_steps<32, 6, 10>(P, ws1, nullptr, sms, st);
+  e = launch_steps<32, 6, 10>(P, ws1, nullptr, sms, st);
+  ee.mark(5, st);
+  return e;
 }
 
 }  // namespace hw

@@ -15,9 +15,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # the .so is git-ignored: build it in-tree when missing or stale (nvcc
     # cross-compiles sm_100a without a GPU)
-    from orthogonal_classifiers_b200.build import build_library, needs_build
-    if needs_build():
-        build_library()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "_oc_b200_build", os.path.join(ROOT, "orthogonal_classifiers_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)  # by path: importing the package needs the library
+    if mod.needs_build():
+        mod.build_library()
 
 
 @pytest.fixture(scope="session")
