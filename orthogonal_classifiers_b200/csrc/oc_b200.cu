@@ -102,6 +102,10 @@ int oc_set_option(const char* key, int value) {
     oc::encode_events().ncalls = 0;
     return OC_OK;
   }
+  if (key && !strcmp(key, "enc_sort")) {
+    oc::hw::sort_pairs() = value;
+    return OC_OK;
+  }
   if (key && !strcmp(key, "enc_hw")) {
     oc::encode_use_hw() = value;
     return OC_OK;
@@ -177,7 +181,7 @@ int oc_encode_batch(const void* images_dev, int in_dtype, int64_t N, int n_pix, 
     float* ws = nullptr;
     {
       std::lock_guard<std::mutex> lk(g_ws_mu);
-      if (int rc = g_enc_ws.ensure((size_t)2 * chunk * oc::kWsStride * sizeof(float))) return rc;
+      if (int rc = g_enc_ws.ensure((size_t)2 * chunk * oc::kWsStride * sizeof(float) + oc::encode_sort_bytes(chunk))) return rc;
       ws = reinterpret_cast<float*>(g_enc_ws.p);
     }
     int rc = oc::encode_fast_launch(P, ws, num_sms(), st);

@@ -501,6 +501,13 @@ __device__ __forceinline__ float* run_steps(const EncodeParams& P, int64_t img, 
 // Kernel for steps [N0, N1).  ws_in: Psi_{N0} of every image ([B][2Q] floats,
 // image stride kWsStride) unless N0 == 0; ws_out: Psi_{N1} unless N1 == 10.
 constexpr int kWsStride = 1024;
+// scratch behind the two Psi buffers for the pairing sort of the half-warp chain:
+// keys (1 byte / image) | perm (int32 / slot, images + padding) | 64 ints of bins
+constexpr int kSortBins = 32;
+inline size_t encode_sort_bytes(int64_t chunk) {
+  return (size_t)((chunk + 255) & ~(int64_t)255) + (size_t)(chunk + 2 * kSortBins) * sizeof(int32_t) +
+         (size_t)4 * kSortBins * sizeof(int32_t) + 256;
+}
 
 template <int DPAD, int N0, int N1>
 __global__ void __launch_bounds__(128, 6) encode_steps_kernel(const __grid_constant__ EncodeParams P,
@@ -606,7 +613,8 @@ inline int& encode_use_hw() {
 }
 namespace hw {
 inline bool supported(const EncodeParams& P);
-inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, int sms, cudaStream_t st);
+inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, void* sort_ws, int64_t chunk,
+                                int sms, cudaStream_t st);
 }  // namespace hw
 
 // ws: 2 * min(N, kEncodeChunk) * kWsStride floats of device scratch.
@@ -633,7 +641,7 @@ inline int encode_fast_launch(const EncodeParams& P0, float* ws, int sms, cudaSt
       ~Restore() { encode_events().on = v; }
     } restore{ev_on};
     if (encode_use_hw() && hw::supported(P)) {
-      e = hw::launch_chain(P, ws0, ws1, sms, st);
+      e = hw::launch_chain(P, ws0, ws1, ws + (size_t)2 * chunk * kWsStride, chunk, sms, st);
       if (e != cudaSuccess) return (int)e;
       continue;
     }

@@ -562,9 +562,13 @@ __host__ __device__ constexpr int ysm_floats(int n) { return (2 << n) * ((2 << n
 // Psi_{n+1} [2B][Q] to psi_out (global if GDST else shared; may alias psi_in
 // when shared: every read of psi_in happens before the first write).
 // ysm: ysm_floats(N) floats of shared memory for this image.
-template <int N, bool GSRC, bool GDST>
-__device__ __forceinline__ void row_step(bool valid, const Out& io, const float* psi_in, float* psi_out,
-                                         float* ysm, float* refl, int lane) {
+// Everything that is only needed after the Jacobi loop (output pointers, key
+// slot) is derived from P (constant bank) and the image index afterwards, so
+// that it does not occupy registers across the loop.
+template <int N, bool GSRC, bool GDST, bool KEYS = false>
+__device__ __forceinline__ void row_step(bool valid, const EncodeParams& P, int64_t im, const float* psi_in,
+                                         float* psi_out, float* ysm, float* refl, int lane,
+                                         uint8_t* keys = nullptr) {
   constexpr int B = 1 << N, Q = 1 << (9 - N);
   constexpr int LOGLP = 4 - N, LP = 1 << LOGLP;
   constexpr int YSTR = 2 * B + 2;
@@ -606,6 +610,7 @@ __device__ __forceinline__ void row_step(bool valid, const Out& io, const float*
   }
   int rT, rS;
   rank16<LOGLP>(nT, nS, lane, rT, rS);
+  const Out io = make_out(P, im, N);
   const int r_rt = io.r_rt, b_rt = io.b_rt;
   const bool kT = nT > thr2 && rT < r_rt;
   const bool kS = nS > thr2 && rS < r_rt;
@@ -618,6 +623,12 @@ __device__ __forceinline__ void row_step(bool valid, const Out& io, const float*
       for (int k = 2 * B + l16; k < io.sv_width; k += 16) io.sv[k] = 0.f;
     }
     if (io.sweeps && l16 == 0) *io.sweeps = sweeps;
+  }
+  if constexpr (KEYS) {
+    // number of kept vectors = non-zero rows of Psi_{n+1} = live slots of the next step
+    const unsigned kt = __ballot_sync(FULL, kT && sub == 0), ks = __ballot_sync(FULL, kS && sub == 0);
+    const int kept = __popc((kt >> hb) & 0xffffu) + __popc((ks >> hb) & 0xffffu);
+    if (valid && l16 == 0) keys[im] = (uint8_t)kept;
   }
   // ---- U[(l,s), k] = (1/n_k) sum_c Psi_n[l][s*Q + c] W_k[c]  -> shared, column-major ----
   float* yT = ysm + slot * YSTR;
@@ -761,26 +772,65 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_head_kernel(cons
   }
   __syncwarp();
   const int64_t im = valid ? img : 0;
-  row_step<0, false, false>(valid, make_out(P, im, 0), buf, buf, ysm, refl, lane);
-  row_step<1, false, false>(valid, make_out(P, im, 1), buf, buf, ysm, refl, lane);
-  row_step<2, false, true>(valid, make_out(P, im, 2), buf, ws_out + (size_t)im * kWsStride, ysm, refl, lane);
+  row_step<0, false, false>(valid, P, im, buf, buf, ysm, refl, lane);
+  row_step<1, false, false>(valid, P, im, buf, buf, ysm, refl, lane);
+  row_step<2, false, true>(valid, P, im, buf, ws_out + (size_t)im * kWsStride, ysm, refl, lane);
 }
 
 // ---- one ROW step from / to the global workspace (N = 3, 4) ----
-template <int N>
+// perm (nullable): slot i of the launch works on image perm[i] (-1 = padding);
+// n_slots_dev holds the number of slots.  keys_out (nullable): per image, the
+// number of vectors this step kept.
+template <int N, bool PERM, bool KEYS>
 __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_row_kernel(const __grid_constant__ EncodeParams P,
                                                                   const float* __restrict__ ws_in,
-                                                                  float* __restrict__ ws_out) {
+                                                                  float* __restrict__ ws_out,
+                                                                  const int32_t* __restrict__ perm,
+                                                                  const int32_t* __restrict__ n_slots_dev,
+                                                                  uint8_t* __restrict__ keys_out) {
   extern __shared__ __align__(16) float smem_f[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int h = lane >> 4;
-  const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
-  const bool valid = img < P.N;
+  const int64_t slot = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
+  int64_t img = slot;
+  if constexpr (PERM) img = slot < *n_slots_dev ? perm[slot] : -1;
+  const bool valid = img >= 0 && img < P.N;
   const int64_t im = valid ? img : 0;
-  row_step<N, true, true>(valid, make_out(P, im, N), ws_in + (size_t)im * kWsStride,
-                          ws_out + (size_t)im * kWsStride, smem_f + (size_t)(warp * 2 + h) * ysm_floats(N),
-                          smem_f + (size_t)kHwWarps * 2 * ysm_floats(N) + (size_t)(warp * 2 + h) * refl_floats(4 - N),
-                          lane);
+  row_step<N, true, true, KEYS>(valid, P, im, ws_in + (size_t)im * kWsStride, ws_out + (size_t)im * kWsStride,
+                                smem_f + (size_t)(warp * 2 + h) * ysm_floats(N),
+                                smem_f + (size_t)kHwWarps * 2 * ysm_floats(N) +
+                                    (size_t)(warp * 2 + h) * refl_floats(4 - N),
+                                lane, keys_out);
+}
+
+// ---- pairing sort: images with the same number of live rows share a warp ----
+// bins[0..31] counts, bins[32..63] starts (even-padded), bins[64..95] cursors, bins[96] = total slots
+__global__ void hw_sort_hist_kernel(const uint8_t* __restrict__ keys, int64_t n, int32_t* __restrict__ bins) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&bins[keys[i] & (kSortBins - 1)], 1);
+}
+__global__ void hw_sort_prefix_kernel(int32_t* __restrict__ bins, int32_t* __restrict__ perm) {
+  if (threadIdx.x == 0) {
+    int start = 0;
+    // descending key: the longest lines are scheduled first
+    for (int b = kSortBins - 1; b >= 0; --b) {
+      const int c = bins[b];
+      bins[kSortBins + b] = start;
+      bins[2 * kSortBins + b] = 0;
+      start += c;
+      if (c & 1) perm[start++] = -1;  // pad the bin to an even number of slots
+    }
+    bins[3 * kSortBins] = start;
+  }
+}
+__global__ void hw_sort_scatter_kernel(const uint8_t* __restrict__ keys, int64_t n, int32_t* __restrict__ bins,
+                                       int32_t* __restrict__ perm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int b = keys[i] & (kSortBins - 1);
+    const int pos = atomicAdd(&bins[2 * kSortBins + b], 1);
+    perm[bins[kSortBins + b] + pos] = (int32_t)i;
+  }
 }
 
 // ---- step 5 (COL): M_5[(s,l), c] = Psi_5[l][s*16 + c], 16 columns of length 64 ----
@@ -932,20 +982,43 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col5_kernel(cons
 inline bool supported(const EncodeParams& P) { return P.L == 10 && P.D > 16; }
 
 // steps 0..5 with the half-warp kernels, 6..9 with the v3 tail
-inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, int sms, cudaStream_t st) {
+inline int& sort_pairs() {
+  static int v = 1;
+  return v;
+}
+inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, void* sort_ws, int64_t chunk,
+                                int sms, cudaStream_t st) {
   const int per_cta = kHwWarps * 2;
   const int grid = (int)((P.N + per_cta - 1) / per_cta);
   const size_t smem_head = (size_t)per_cta * (1024 + ysm_floats(2) + refl_floats(3)) * sizeof(float);
   const size_t smem3 = (size_t)per_cta * (ysm_floats(3) + refl_floats(1)) * sizeof(float);
   const size_t smem4 = (size_t)per_cta * (ysm_floats(4) + refl_floats(0)) * sizeof(float);
   const size_t smem5 = (size_t)per_cta * refl_floats(1) * sizeof(float);
+  uint8_t* keys = reinterpret_cast<uint8_t*>(sort_ws);
+  int32_t* perm = reinterpret_cast<int32_t*>(keys + ((chunk + 255) & ~(int64_t)255));
+  int32_t* bins = perm + chunk + 2 * kSortBins;
+  const bool sorted = sort_pairs() != 0;
   EncodeEvents& ee = encode_events();
   ee.mark(0, st);
   hw_head_kernel<<<grid, kHwWarps * 32, smem_head, st>>>(P, ws0);
   ee.mark(1, st);
-  hw_row_kernel<3><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1);
+  if (sorted)
+    hw_row_kernel<3, false, true><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1, nullptr, nullptr, keys);
+  else
+    hw_row_kernel<3, false, false><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1, nullptr, nullptr, nullptr);
   ee.mark(2, st);
-  hw_row_kernel<4><<<grid, kHwWarps * 32, smem4, st>>>(P, ws1, ws0);
+  if (sorted) {
+    // step 4 costs (live rows) x (sweeps) per WARP: pair images with equal numbers of live rows
+    cudaMemsetAsync(bins, 0, (size_t)4 * kSortBins * sizeof(int32_t), st);
+    const int tb = 256, gb = (int)((P.N + tb - 1) / tb);
+    hw_sort_hist_kernel<<<gb, tb, 0, st>>>(keys, P.N, bins);
+    hw_sort_prefix_kernel<<<1, 32, 0, st>>>(bins, perm);
+    hw_sort_scatter_kernel<<<gb, tb, 0, st>>>(keys, P.N, bins, perm);
+    const int grid4 = (int)((P.N + kSortBins + per_cta - 1) / per_cta);
+    hw_row_kernel<4, true, false><<<grid4, kHwWarps * 32, smem4, st>>>(P, ws1, ws0, perm, bins + 3 * kSortBins, nullptr);
+  } else {
+    hw_row_kernel<4, false, false><<<grid, kHwWarps * 32, smem4, st>>>(P, ws1, ws0, nullptr, nullptr, nullptr);
+  }
   ee.mark(3, st);
   hw_col5_kernel<<<grid, kHwWarps * 32, smem5, st>>>(P, ws0, ws1);
   ee.mark(4, st);
