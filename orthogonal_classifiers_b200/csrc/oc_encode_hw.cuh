@@ -28,10 +28,6 @@
 #pragma once
 #include "oc_encode_fast.cuh"
 
-#ifndef OC_HW_LIFT
-#define OC_HW_LIFT 0  // experiment: in-place lifting rotations (measured: no faster, see profiles/encode_r1.md)
-#endif
-
 namespace oc {
 namespace hw {
 
@@ -44,16 +40,6 @@ __device__ __forceinline__ float hsum2(u64 v) {
   float lo, hi;
   unpack2(v, lo, hi);
   return lo + hi;
-}
-// 64-bit shared-memory accesses the compiler must not fuse into 128-bit ones
-// (register pairs of the vector arrays are not quad-aligned: fusing costs MOVs)
-__device__ __forceinline__ void sts64(unsigned addr, u64 v) {
-  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
-}
-__device__ __forceinline__ u64 lds64(unsigned addr) {
-  u64 v;
-  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
-  return v;
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -124,323 +110,63 @@ __device__ __forceinline__ void rotate16(u64 (&a)[16], u64 (&b)[16], float& na, 
   nb = n_second;
 }
 
-// Fast (scaled) rotation: the true vectors are a = da * A, b = db * B with A, B
-// the stored arrays.  With t = tan(theta) the rotated pair is
-//   first'  = c (b + t a) = (c db) (B + beta A),    beta  = t da / db
-//   second' = c (a - t b) = (c da) (A - alpha B),   alpha = t db / da
-// so the cosine goes into the scale factors and the update is ONE packed FMA
-// per output pair instead of two.  Only t sits on the critical path (two
-// dependent MUFUs); c = (1 + t^2)^(-1/2) is refined by a Newton step from the t
-// actually used, so the transformation is orthogonal to ~1 ulp whatever the
-// error of the approximate sqrt / rcp.  `hold`: exact no-op for this lane.
-template <int LOGLP>
-__device__ __forceinline__ void frot16(u64 (&a)[16], u64 (&b)[16], float& na, float& nb, float& da, float& db,
-                                       float thr2, bool hold, unsigned hmask, bool& again) {
-  const float r_ab = da * rcp_approx(db);  // da / db, db / da: off the critical path
-  const float r_ba = db * rcp_approx(da);
-  const float dd = da * db;
-  const float ab = dot16<LOGLP>(a, b) * dd;
-  const float aa = na, bb = nb;
-  const float d = aa * bb;
-  const float ab2 = ab * ab;
-  const bool rot = (ab2 > kTol2 * d) && (aa > thr2) && (bb > thr2) && !hold;
-  again = again || (rot && ab2 > kQStop2 * d);
-  const float delta = bb - aa;
-  const float gamma = rot ? ab + ab : 0.f;
-  const float w = sqrt_approx(fmaf(delta, delta, gamma * gamma));
-  const float den = fabsf(delta) + w;
-  const float sg = copysignf(gamma, delta * gamma);
-  const float t = rot ? sg * rcp_approx(den) : 0.f;
-  const float beta = t * r_ab, alpha = t * r_ba;
-  const float X = fmaf(t, t, 1.f);
-  float c = rsqrt_approx(X);
-  c = c * fmaf(-0.5f * X, c * c, 1.5f);
-  bool lost = false;
-  if (!hold) {
-    const u64 b2 = pack2(beta, beta), na2 = pack2(-alpha, -alpha);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const u64 x = a[e], y = b[e];
-      a[e] = fma2(b2, x, y);
-      b[e] = fma2(na2, y, x);
-    }
-    const float n_first = fmaf(t, ab, bb), n_second = fmaf(-t, ab, aa);
-    lost = rot && (n_second < kCancel * aa || n_first < kCancel * bb);
-    na = n_first;
-    nb = n_second;
-    const float d_first = c * db, d_second = c * da;
-    da = d_first;
-    db = d_second;
-  }
-  const unsigned lostmask = __ballot_sync(FULL, lost);
-  if (lostmask) {  // warp-uniform, rare after the first sweeps
-    const float f1 = dot16<LOGLP>(a, a) * da * da, f2 = dot16<LOGLP>(b, b) * db * db;
-    if (lost) {
-      na = f1;
-      nb = f2;
-    }
-  }
-}
-
-// One-sided Jacobi, odd-even ordering, on the 2*M vectors of each half-warp.
-// mlive: live slots of THIS half (0 = nothing to do); mlive_max: warp maximum.
-#ifndef OC_HW_FAST_ROT
-#define OC_HW_FAST_ROT 0
-#endif
-#ifndef OC_HW_UNROLL
-#define OC_HW_UNROLL 1
-#endif
-constexpr int kHwUnroll = OC_HW_UNROLL;
-template <int LOGLP, int NE = 16>
+// One-sided Jacobi, odd-even ordering, on the 2*M vectors of each GROUP of
+// G = 2^LOGG lanes (one image per group; G = 16 for steps 0..5).
+// mlive: live slots of THIS group (0 = nothing to do); mlive_max: warp maximum.
+template <int LOGLP, int NE = 16, int LOGG = 4>
 __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, float& nS, float thr2,
                                         int lane, int mlive, int mlive_max) {
   constexpr int LP = 1 << LOGLP;
-  constexpr int M = 16 >> LOGLP;
-  const int l16 = lane & 15, hb = lane & 16;
-  const int slot = l16 >> LOGLP;
-  const int src_dn = hb | ((l16 + LP) & 15);
-  const int src_up = hb | ((l16 - LP) & 15);
+  constexpr int G = 1 << LOGG;
+  constexpr int M = G >> LOGLP;
+  const int lg = lane & (G - 1), gb = lane & ~(G - 1);
+  const int slot = lg >> LOGLP;
+  const int src_dn = gb | ((lg + LP) & (G - 1));
+  const int src_up = gb | ((lg - LP) & (G - 1));
   const bool idleB = slot >= mlive - 1;
-  const unsigned hmask = 0xffffu << hb;
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gb;
   int sweeps = 0;
   bool done = mlive == 0;
-#if OC_HW_FAST_ROT
-  float dT = 1.f, dS = 1.f;
-#endif
 #pragma unroll 1
   for (int sw = 0; sw < kMaxSweeps; ++sw) {
     bool again = false;
     bool lostf = false;
     {
-#if OC_HW_FAST_ROT
-      // fold the scale factors back into the data before refreshing the norms
-      const u64 t2 = pack2(dT, dT), s2 = pack2(dS, dS);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        T[e] = mul2(T[e], t2);
-        S[e] = mul2(S[e], s2);
-      }
-      dT = dS = 1.f;
-#endif
       const float fT = dot16<LOGLP, NE>(T, T), fS = dot16<LOGLP, NE>(S, S);
       if (!done) {
         nT = fT;
         nS = fS;
       }
     }
-#pragma unroll kHwUnroll
+#pragma unroll 1
     for (int rr = 0; rr < mlive_max; ++rr) {
-      const bool off = done || rr >= mlive;  // this half has nothing left to do in this round
-#if OC_HW_FAST_ROT
-      frot16<LOGLP>(T, S, nT, nS, dT, dS, thr2, off, hmask, again);
-#else
+      const bool off = done || rr >= mlive;  // this group has nothing left to do in this round
       rotate16<LOGLP, NE>(T, S, nT, nS, thr2, off, lostf, again);
-#endif
       if (M > 1) {
 #pragma unroll
         for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_dn);
         float nR = __shfl_sync(FULL, nT, src_dn);
-#if OC_HW_FAST_ROT
-        float dR = __shfl_sync(FULL, dT, src_dn);
-        frot16<LOGLP>(S, T, nS, nR, dS, dR, thr2, off || idleB, hmask, again);
-        dT = __shfl_sync(FULL, dR, src_up);
-#else
         rotate16<LOGLP, NE>(S, T, nS, nR, thr2, off || idleB, lostf, again);
-#endif
 #pragma unroll
         for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_up);
         nT = __shfl_sync(FULL, nR, src_up);
       }
-#if !OC_HW_FAST_ROT
       {
         const unsigned lostmask = __ballot_sync(FULL, lostf);
         if (lostmask) {  // warp-uniform, rare after the first sweeps
           const float fT = dot16<LOGLP, NE>(T, T), fS = dot16<LOGLP, NE>(S, S);
-          if (lostmask & hmask) {  // only the half that cancelled takes the refreshed norms
+          if (lostmask & gmask) {  // only the group that cancelled takes the refreshed norms
             nT = fT;
             nS = fS;
           }
           lostf = false;
         }
       }
-#endif
     }
     if (!done) ++sweeps;
     const unsigned b = __ballot_sync(FULL, again);
-    if (M == 1 || mlive <= 1 || !(b & hmask)) done = true;
+    if (M == 1 || mlive <= 1 || !(b & gmask)) done = true;
     if (__all_sync(FULL, done)) break;
-  }
-#if OC_HW_FAST_ROT
-  {
-    const u64 t2 = pack2(dT, dT), s2 = pack2(dS, dS);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      T[e] = mul2(T[e], t2);
-      S[e] = mul2(S[e], s2);
-    }
-  }
-#endif
-  return sweeps;
-}
-
-// ---------------------------------------------------------------------------
-// In-place ("lifting") form of the fast rotation.  With x at the first and y at
-// the second position of the pair, t = tan(theta), c = cos(theta):
-//     y <- y + beta x            beta  = t dx / dy          (scale dy <- c dy)
-//     x <- x - alpha y_new       alpha = t c^2 dy / dx      (scale dx <- dx / c)
-// leaves c (y + t x) in y's registers and c (x - t y) in x's, two packed FMAs
-// per element pair, no temporaries and no register renaming; beta = alpha = 0
-// is an exact no-op, so holding a lane costs nothing.  The vectors do NOT swap
-// registers; the position swap of the odd-even ordering is done by the data
-// movement in jacobi16_lift.
-template <int LOGLP>
-__device__ __forceinline__ void lift16(u64 (&x)[16], u64 (&y)[16], float& nx, float& ny, float& dx, float& dy,
-                                       float thr2, bool hold, bool& lostf, bool& again) {
-  const float r_xy = dx * rcp_approx(dy);  // off the critical path
-  const float r_yx = dy * rcp_approx(dx);
-  const float ab = dot16<LOGLP>(x, y) * (dx * dy);
-  const float aa = nx, bb = ny;
-  const float d = aa * bb;
-  const float ab2 = ab * ab;
-  const bool rot = (ab2 > kTol2 * d) && (aa > thr2) && (bb > thr2) && !hold;
-  again = again || (rot && ab2 > kQStop2 * d);
-  const float delta = bb - aa;
-  const float gamma = rot ? ab + ab : 0.f;
-  const float w = sqrt_approx(fmaf(delta, delta, gamma * gamma));
-  const float den = fabsf(delta) + w;
-  const float sg = copysignf(gamma, delta * gamma);
-  const float t = rot ? sg * rcp_approx(den) : 0.f;
-  const float X = fmaf(t, t, 1.f);
-  float c = rsqrt_approx(X);
-  c = c * fmaf(-0.5f * X, c * c, 1.5f);  // Newton: the transformation is orthogonal to ~1 ulp for the t used
-  const float beta = rot ? t * r_xy : 0.f;
-  const float alpha = rot ? t * r_yx * (c * c) : 0.f;
-  const u64 b2 = pack2(beta, beta), na2 = pack2(-alpha, -alpha);
-#pragma unroll
-  for (int e = 0; e < 16; ++e) y[e] = fma2(b2, x[e], y[e]);
-#pragma unroll
-  for (int e = 0; e < 16; ++e) x[e] = fma2(na2, y[e], x[e]);
-  const float n_y = fmaf(t, ab, bb), n_x = fmaf(-t, ab, aa);  // t = 0: unchanged
-  lostf = lostf || (rot && (n_x < kCancel * aa || n_y < kCancel * bb));
-  nx = n_x;
-  ny = n_y;
-  dy = rot ? c * dy : dy;
-  dx = rot ? dx * (X * c) : dx;
-}
-
-// Odd-even ordering with the lifting rotation.  Register sets P, Q of slot k
-// hold line positions (2k, 2k+1) between iterations.  One iteration:
-//   A: rotate (P_k, Q_k)                    -> logically P = second, Q = first
-//   Q moves one slot down (lane k gets first_{k+1})
-//   B: rotate (P_k, Q_k) = (second_k, first_{k+1})
-//   P moves one slot up (lane k+1 gets its new first position)
-// The two vectors that sit out round B (first_0 and second_{m-1}) change sets at
-// the line ends through a per-lane scratch row in shared memory (written and
-// read by the same lane).  A half that is finished, or past its own line length
-// in this sweep, neither rotates nor moves (shuffle source = itself), so its
-// state never depends on the image sharing its warp.
-// refl: refl_floats(LOGLP) floats of shared memory of this IMAGE (each lane uses its own rows).
-template <int LOGLP>
-__device__ __forceinline__ int jacobi16_lift(u64 (&P)[16], u64 (&Q)[16], float& nP, float& nQ, float thr2,
-                                             int lane, int mlive, int mlive_max, float* refl) {
-  constexpr int LP = 1 << LOGLP;
-  constexpr int M = 16 >> LOGLP;
-  const int l16 = lane & 15, hb = lane & 16;
-  const int slot = l16 >> LOGLP;
-  const int src_dn = hb | ((l16 + LP) & 15);
-  const int src_up = hb | ((l16 - LP) & 15);
-  const bool live = slot < mlive;
-  const bool first = live && slot == 0, last = live && slot == mlive - 1;
-  const bool idleB = slot >= mlive - 1;
-  const unsigned hmask = 0xffffu << hb;
-  int sweeps = 0;
-  bool done = mlive == 0;
-  float dP = 1.f, dQ = 1.f;
-  const unsigned rq = (unsigned)__cvta_generic_to_shared(refl + (l16 & (LP - 1)) * 32);
-  const unsigned rp = (unsigned)__cvta_generic_to_shared(refl + (LP + (l16 & (LP - 1))) * 32);
-#pragma unroll 1
-  for (int sw = 0; sw < kMaxSweeps; ++sw) {
-    bool again = false;
-    bool lostf = false;
-    {
-      // fold the scale factors back into the data, refresh the norms
-      const u64 p2 = pack2(dP, dP), q2 = pack2(dQ, dQ);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        P[e] = mul2(P[e], p2);
-        Q[e] = mul2(Q[e], q2);
-      }
-      dP = dQ = 1.f;
-      const float fP = dot16<LOGLP>(P, P), fQ = dot16<LOGLP>(Q, Q);
-      if (!done && live) {
-        nP = fP;
-        nQ = fQ;
-      }
-    }
-#pragma unroll 1
-    for (int rr = 0; rr < mlive_max; ++rr) {
-      const bool off = done || rr >= mlive;  // this half sits this round pair out
-      lift16<LOGLP>(P, Q, nP, nQ, dP, dQ, thr2, off || !live, lostf, again);
-      if (M > 1) {
-        const bool mvf = first && !off, mvl = last && !off;
-        const int sq = off ? lane : src_dn, sp = off ? lane : src_up;
-        const float keepN = nQ, keepD = dQ;
-        if (mvf) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) sts64(rq + 8 * e, Q[e]);
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) Q[e] = shfl2(Q[e], sq);
-        nQ = __shfl_sync(FULL, nQ, sq);
-        dQ = __shfl_sync(FULL, dQ, sq);
-        lift16<LOGLP>(P, Q, nP, nQ, dP, dQ, thr2, off || idleB, lostf, again);
-        const float keepN2 = nP, keepD2 = dP;
-        if (mvl) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) sts64(rp + 8 * e, P[e]);
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) P[e] = shfl2(P[e], sp);
-        nP = __shfl_sync(FULL, nP, sp);
-        dP = __shfl_sync(FULL, dP, sp);
-        if (mvf) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) P[e] = lds64(rq + 8 * e);
-          nP = keepN;
-          dP = keepD;
-        }
-        if (mvl) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) Q[e] = lds64(rp + 8 * e);
-          nQ = keepN2;
-          dQ = keepD2;
-        }
-      }
-      {
-        const unsigned lostmask = __ballot_sync(FULL, lostf);
-        if (lostmask) {  // warp-uniform, rare after the first sweeps
-          const float fP = dot16<LOGLP>(P, P) * dP * dP, fQ = dot16<LOGLP>(Q, Q) * dQ * dQ;
-          if ((lostmask & hmask) && live && !off) {  // only the half that cancelled takes the refreshed norms
-            nP = fP;
-            nQ = fQ;
-          }
-          lostf = false;
-        }
-      }
-    }
-    if (!done) ++sweeps;
-    const unsigned b = __ballot_sync(FULL, again);
-    if (M == 1 || mlive <= 1 || !(b & hmask)) done = true;
-    if (__all_sync(FULL, done)) break;
-  }
-  {
-    // dead slots may have collected copies of the end vectors: clear them
-    const u64 p2 = live ? pack2(dP, dP) : 0ull, q2 = live ? pack2(dQ, dQ) : 0ull;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      P[e] = live ? mul2(P[e], p2) : 0ull;
-      Q[e] = live ? mul2(Q[e], q2) : 0ull;
-    }
   }
   return sweeps;
 }
@@ -513,10 +239,11 @@ __device__ __forceinline__ void polish16(u64 (&T)[B2], u64 (&S)[B2], float& kT, 
 }
 
 // stable descending rank of this lane's two vectors among the NV = 2*M of its half
-template <int LOGLP>
+template <int LOGLP, int LOGG = 4>
 __device__ __forceinline__ void rank16(float nT, float nS, int lane, int& rT, int& rS) {
-  constexpr int NV = 2 * (16 >> LOGLP);
-  const int hb = lane & 16, slot = (lane & 15) >> LOGLP;
+  constexpr int G = 1 << LOGG;
+  constexpr int NV = 2 * (G >> LOGLP);
+  const int hb = lane & ~(G - 1), slot = (lane & (G - 1)) >> LOGLP;
   const int pT = 2 * slot, pS = pT + 1;
   rT = 0;
   rS = 0;
@@ -528,9 +255,10 @@ __device__ __forceinline__ void rank16(float nT, float nS, int lane, int& rT, in
   }
 }
 
-__device__ __forceinline__ float half_sum(float v) {
+template <int LOGG = 4>
+__device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  for (int o = (1 << LOGG) >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
 
@@ -553,8 +281,6 @@ __device__ __forceinline__ Out make_out(const EncodeParams& P, int64_t img, int 
   return o;
 }
 
-// floats of shared memory one image needs for the end-of-line scratch of jacobi16_lift
-__host__ __device__ constexpr int refl_floats(int loglp) { return OC_HW_LIFT ? (64 << loglp) : 0; }
 // floats of shared memory one image needs for the U columns of ROW step n
 __host__ __device__ constexpr int ysm_floats(int n) { return (2 << n) * ((2 << n) + 2); }
 
@@ -567,7 +293,7 @@ __host__ __device__ constexpr int ysm_floats(int n) { return (2 << n) * ((2 << n
 // that it does not occupy registers across the loop.
 template <int N, bool GSRC, bool GDST, bool KEYS = false>
 __device__ __forceinline__ void row_step(bool valid, const EncodeParams& P, int64_t im, const float* psi_in,
-                                         float* psi_out, float* ysm, float* refl, int lane,
+                                         float* psi_out, float* ysm, int lane,
                                          uint8_t* keys = nullptr) {
   constexpr int B = 1 << N, Q = 1 << (9 - N);
   constexpr int LOGLP = 4 - N, LP = 1 << LOGLP;
@@ -589,7 +315,7 @@ __device__ __forceinline__ void row_step(bool valid, const EncodeParams& P, int6
     }
   }
   float nT = dot16<LOGLP>(T, T), nS = dot16<LOGLP>(S, S);
-  const float fro = half_sum(sub == 0 ? nT + nS : 0.f);
+  const float fro = group_sum(sub == 0 ? nT + nS : 0.f);
   const float thr2 = kFloor2 * fro;
   // live slots: rows dropped by the previous step / padding are exactly zero and sit at the end
   const unsigned livemask = __ballot_sync(FULL, (nT + nS) > 0.f);
@@ -600,11 +326,7 @@ __device__ __forceinline__ void row_step(bool valid, const EncodeParams& P, int6
   const int mlive_max = ml0 > ml1 ? ml0 : ml1;
   int sweeps = 0;
   if (mlive_max > 0) {
-#if OC_HW_LIFT
-    sweeps = jacobi16_lift<LOGLP>(T, S, nT, nS, thr2, lane, mlive, mlive_max, refl);
-#else
     sweeps = jacobi16<LOGLP>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
-#endif
     nT = dot16<LOGLP>(T, T);
     nS = dot16<LOGLP>(S, S);
   }
@@ -743,7 +465,6 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_head_kernel(cons
   const bool valid = img < P.N;
   float* buf = smem_f + (size_t)(warp * 2 + h) * 1024;
   float* ysm = smem_f + (size_t)kHwWarps * 2 * 1024 + (size_t)(warp * 2 + h) * ysm_floats(2);
-  float* refl = smem_f + (size_t)kHwWarps * 2 * (1024 + ysm_floats(2)) + (size_t)(warp * 2 + h) * refl_floats(3);
   // stage the tail-padded image (tools.py:218-220: flat padding, pixel i -> amplitude i)
   {
     const char* src = reinterpret_cast<const char*>(P.images);
@@ -772,9 +493,9 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_head_kernel(cons
   }
   __syncwarp();
   const int64_t im = valid ? img : 0;
-  row_step<0, false, false>(valid, P, im, buf, buf, ysm, refl, lane);
-  row_step<1, false, false>(valid, P, im, buf, buf, ysm, refl, lane);
-  row_step<2, false, true>(valid, P, im, buf, ws_out + (size_t)im * kWsStride, ysm, refl, lane);
+  row_step<0, false, false>(valid, P, im, buf, buf, ysm, lane);
+  row_step<1, false, false>(valid, P, im, buf, buf, ysm, lane);
+  row_step<2, false, true>(valid, P, im, buf, ws_out + (size_t)im * kWsStride, ysm, lane);
 }
 
 // ---- one ROW step from / to the global workspace (N = 3, 4) ----
@@ -797,10 +518,7 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_row_kernel(const
   const bool valid = img >= 0 && img < P.N;
   const int64_t im = valid ? img : 0;
   row_step<N, true, true, KEYS>(valid, P, im, ws_in + (size_t)im * kWsStride, ws_out + (size_t)im * kWsStride,
-                                smem_f + (size_t)(warp * 2 + h) * ysm_floats(N),
-                                smem_f + (size_t)kHwWarps * 2 * ysm_floats(N) +
-                                    (size_t)(warp * 2 + h) * refl_floats(4 - N),
-                                lane, keys_out);
+                                smem_f + (size_t)(warp * 2 + h) * ysm_floats(N), lane, keys_out);
 }
 
 // ---- pairing sort: images with the same number of live rows share a warp ----
@@ -833,119 +551,142 @@ __global__ void hw_sort_scatter_kernel(const uint8_t* __restrict__ keys, int64_t
   }
 }
 
-// ---- step 5 (COL): M_5[(s,l), c] = Psi_5[l][s*16 + c], 16 columns of length 64 ----
-__global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col5_kernel(const __grid_constant__ EncodeParams P,
-                                                                   const float* __restrict__ ws_in,
-                                                                   float* __restrict__ ws_out) {
-  constexpr int LOGLP = 1;
-  extern __shared__ __align__(16) float smem_f[];
+// ---- COL steps 5, 6, 7: M_n[(s,l), c] = Psi_n[l][s*Q + c], Q = 2^(9-n) columns of
+//      length 2B = 2^(11-n).  Slot k owns columns (2k, 2k+1); one image per
+//      group of G lanes:  n  cols x len  slots  lanes/slot  G   images/warp
+//                         5   16 x 64      8        2      16       2
+//                         6    8 x 32      4        1       4       8
+//                         7    4 x 16      2        1       2      16
+//      Converged columns are U.S; A_n = U, Psi_{n+1} = U^T M_n.
+template <int N>
+struct ColShape {
+  static constexpr int B = 1 << (10 - N), Q = 1 << (9 - N);
+  static constexpr int LOGLP = N == 5 ? 1 : 0, LP = 1 << LOGLP;
+  static constexpr int M = Q / 2, G = M * LP, LOGG = clog2(G);
+  static constexpr int EL = 2 * B / LP;  // elements per lane and vector (32, 32, 16)
+  static constexpr int NE = EL / 2;      // packed pairs
+  static constexpr int IPW = 32 / G;     // images per warp
+};
+
+template <int N>
+__global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col_kernel(const __grid_constant__ EncodeParams P,
+                                                                           const float* __restrict__ ws_in,
+                                                                           float* __restrict__ ws_out) {
+  using C = ColShape<N>;
+  constexpr int B = C::B, Q = C::Q, LOGLP = C::LOGLP, LP = C::LP, M = C::M, G = C::G, LOGG = C::LOGG;
+  constexpr int EL = C::EL, NE = C::NE, IPW = C::IPW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int l16 = lane & 15, h = lane >> 4;
-  float* refl = smem_f + (size_t)(warp * 2 + h) * refl_floats(LOGLP);
-  const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
+  const int lg = lane & (G - 1), grp = lane >> LOGG;
+  const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * IPW + grp;
   const bool valid = img < P.N;
   const int64_t im = valid ? img : 0;
-  const Out io = make_out(P, im, 5);
-  const float* psi = ws_in + (size_t)im * kWsStride;  // [32][32]
-  const int slot = l16 >> 1, s = l16 & 1;
+  const Out io = make_out(P, im, N);
+  const float* psi = ws_in + (size_t)im * kWsStride;  // [B][2Q]
+  const int slot = lg >> LOGLP, sub = lg & (LP - 1);
+  // this lane's elements e = sub*EL + i, i < EL  <->  (s, l) = (e / B, e % B);
+  // packed pair j holds e = e0 + 2j, e0 + 2j + 1 (same s: B is even)
+  const int e0 = sub * EL;
   u64 T[16], S[16];
-  {
-    const float* pc = psi + s * 16 + 2 * slot;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < 16; ++j) T[j] = S[j] = 0ull;
+  {
+    const float* pc = psi + 2 * slot;
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      const int e = e0 + 2 * j, sj = e / B, lj = e % B;
       float2 v0 = make_float2(0.f, 0.f), v1 = v0;
       if (valid) {
-        v0 = __ldg(reinterpret_cast<const float2*>(pc + (2 * j) * 32));
-        v1 = __ldg(reinterpret_cast<const float2*>(pc + (2 * j + 1) * 32));
+        v0 = __ldg(reinterpret_cast<const float2*>(pc + lj * 2 * Q + sj * Q));
+        v1 = __ldg(reinterpret_cast<const float2*>(pc + (lj + 1) * 2 * Q + sj * Q));
       }
       T[j] = pack2(v0.x, v1.x);
       S[j] = pack2(v0.y, v1.y);
     }
   }
-  float nT = dot16<LOGLP>(T, T), nS = dot16<LOGLP>(S, S);
-  const float fro = half_sum(s == 0 ? nT + nS : 0.f);
+  float nT = dot16<LOGLP, NE>(T, T), nS = dot16<LOGLP, NE>(S, S);
+  const float fro = group_sum<LOGG>(sub == 0 ? nT + nS : 0.f);
   const float thr2 = kFloor2 * fro;
-  const unsigned fmask = __ballot_sync(FULL, fro > 0.f);
-  const int mlive = fro > 0.f ? 8 : 0;
-  const int mlive_max = fmask ? 8 : 0;
+  const int mlive = fro > 0.f ? M : 0;
+  const int mlive_max = __any_sync(FULL, fro > 0.f) ? M : 0;
   int sweeps = 0;
   if (mlive_max > 0) {
-#if OC_HW_LIFT
-    sweeps = jacobi16_lift<LOGLP>(T, S, nT, nS, thr2, lane, mlive, mlive_max, refl);
-#else
-    // rows l >= rank(bond 5) of Psi_5 are zero (<= 24 for 784 pixels): when the
-    // last 4 packed pairs (l >= 24) are zero in the whole warp, skip them
-    bool tailnz = false;
+    if constexpr (N == 5) {
+      // rows l >= rank(bond 5) of Psi_5 are zero (<= 24 for 784 pixels): when the
+      // last 4 packed pairs (l >= 24) are zero in the whole warp, skip them
+      bool tailnz = false;
 #pragma unroll
-    for (int j = 12; j < 16; ++j) tailnz = tailnz || (T[j] | S[j]) != 0ull;
-    if (__any_sync(FULL, tailnz))
-      sweeps = jacobi16<LOGLP>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
-    else
-      sweeps = jacobi16<LOGLP, 12>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
-#endif
-    nT = dot16<LOGLP>(T, T);
-    nS = dot16<LOGLP>(S, S);
+      for (int j = 12; j < 16; ++j) tailnz = tailnz || (T[j] | S[j]) != 0ull;
+      if (__any_sync(FULL, tailnz))
+        sweeps = jacobi16<LOGLP, 16, LOGG>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+      else
+        sweeps = jacobi16<LOGLP, 12, LOGG>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+    } else {
+      sweeps = jacobi16<LOGLP, NE, LOGG>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+    }
+    nT = dot16<LOGLP, NE>(T, T);
+    nS = dot16<LOGLP, NE>(S, S);
   }
   int rT, rS;
-  rank16<LOGLP>(nT, nS, lane, rT, rS);
+  rank16<LOGLP, LOGG>(nT, nS, lane, rT, rS);
   const int r_rt = io.r_rt, b_rt = io.b_rt;
   const bool kT = nT > thr2 && rT < r_rt;
   const bool kS = nS > thr2 && rS < r_rt;
   if (valid) {
     if (io.sv) {
-      if (s == 0) {
+      if (sub == 0) {
         if (rT < io.sv_width) io.sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
         if (rS < io.sv_width) io.sv[rS] = nS > thr2 ? sqrtf(nS) : 0.f;
       }
-      for (int k = 16 + l16; k < io.sv_width; k += 16) io.sv[k] = 0.f;
+      for (int k = Q + lg; k < io.sv_width; k += G) io.sv[k] = 0.f;
     }
-    if (io.sweeps && l16 == 0) *io.sweeps = sweeps;
+    if (io.sweeps && lg == 0) *io.sweeps = sweeps;
   }
   // U = normalised columns
   const float iT = kT ? rsqrtf(nT) : 0.f;
   const float iS = kS ? rsqrtf(nS) : 0.f;
   const u64 iT2 = pack2(iT, iT), iS2 = pack2(iS, iS);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < NE; ++j) {
     T[j] = mul2(T[j], iT2);
     S[j] = mul2(S[j], iS2);
   }
-  // A_5[(s*b + l), rank]
+  // A_n[(s*b + l), rank]
   if (valid) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < NE; ++j) {
       float t0, t1, s0, s1;
       unpack2(T[j], t0, t1);
       unpack2(S[j], s0, s1);
-      const int l0 = 2 * j, l1 = 2 * j + 1;
-      if (l0 < b_rt) {
-        if (rT < r_rt) io.A[(s * b_rt + l0) * r_rt + rT] = t0;
-        if (rS < r_rt) io.A[(s * b_rt + l0) * r_rt + rS] = s0;
+      const int e = e0 + 2 * j, sj = e / B, la = e % B, lb = la + 1;
+      if (la < b_rt) {
+        if (rT < r_rt) io.A[(sj * b_rt + la) * r_rt + rT] = t0;
+        if (rS < r_rt) io.A[(sj * b_rt + la) * r_rt + rS] = s0;
       }
-      if (l1 < b_rt) {
-        if (rT < r_rt) io.A[(s * b_rt + l1) * r_rt + rT] = t1;
-        if (rS < r_rt) io.A[(s * b_rt + l1) * r_rt + rS] = s1;
+      if (lb < b_rt) {
+        if (rT < r_rt) io.A[(sj * b_rt + lb) * r_rt + rT] = t1;
+        if (rS < r_rt) io.A[(sj * b_rt + lb) * r_rt + rS] = s1;
       }
     }
   }
-  // Psi_6[r][c'] = sum_{s,l} U[(s,l)][r] Psi_5[l][s*16 + c']
-  u64 aT[8], aS[8];
+  // Psi_{n+1}[r][c'] = sum_e U[e][r] M[e][c'],  M[(s,l)][c'] = Psi_n[l][s*Q + c']
+  constexpr int Q2 = Q / 2;  // packed pairs per row of M
+  u64 aT[Q2], aS[Q2];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) aT[q] = aS[q] = 0ull;
+  for (int q = 0; q < Q2; ++q) aT[q] = aS[q] = 0ull;
   {
-    const float* pm = psi + s * 16;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < NE; ++j) {
       float t0, t1, s0, s1;
       unpack2(T[j], t0, t1);
       unpack2(S[j], s0, s1);
+      const int e = e0 + 2 * j, sj = e / B, lj = e % B;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const u64 ut = p ? pack2(t1, t1) : pack2(t0, t0);
         const u64 us = p ? pack2(s1, s1) : pack2(s0, s0);
-        const float* row = pm + (2 * j + p) * 32;
+        const float* row = psi + (lj + p) * 2 * Q + sj * Q;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
+        for (int q4 = 0; q4 < Q / 4; ++q4) {
           float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
           if (valid) m = ldg4(row + 4 * q4);
           const u64 m0 = pack2(m.x, m.y), m1 = pack2(m.z, m.w);
@@ -957,25 +698,136 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col5_kernel(cons
       }
     }
   }
-  // sum the two s-halves (lane pairs), then lane s = 0 writes row rT, lane s = 1 row rS
+  if constexpr (LP == 2) {
+    // sum the two element halves (lane pairs)
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    aT[q] = add2(aT[q], shfl2(aT[q], lane ^ 1));
-    aS[q] = add2(aS[q], shfl2(aS[q], lane ^ 1));
+    for (int q = 0; q < Q2; ++q) {
+      aT[q] = add2(aT[q], shfl2(aT[q], lane ^ 1));
+      aS[q] = add2(aS[q], shfl2(aS[q], lane ^ 1));
+    }
   }
   if (valid) {
     float* out = ws_out + (size_t)im * kWsStride;
-    const int r = s ? rS : rT;
-    if (r < 16) {
+    // LP == 2: lane sub = 0 writes row rT, sub = 1 row rS; LP == 1: the lane writes both
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        float4 v;
-        const u64 a0 = s ? aS[2 * q4] : aT[2 * q4], a1 = s ? aS[2 * q4 + 1] : aT[2 * q4 + 1];
-        unpack2(a0, v.x, v.y);
-        unpack2(a1, v.z, v.w);
-        *reinterpret_cast<float4*>(out + r * 16 + 4 * q4) = v;
+    for (int w = 0; w < 2; ++w) {
+      if (LP == 2 && w != sub) continue;
+      const int r = w ? rS : rT;
+      if (r < Q) {
+#pragma unroll
+        for (int q4 = 0; q4 < Q / 4; ++q4) {
+          float4 v;
+          const u64 a0 = w ? aS[2 * q4] : aT[2 * q4], a1 = w ? aS[2 * q4 + 1] : aT[2 * q4 + 1];
+          unpack2(a0, v.x, v.y);
+          unpack2(a1, v.z, v.w);
+          *reinterpret_cast<float4*>(out + r * Q + 4 * q4) = v;
+        }
       }
     }
+  }
+}
+
+// ---- steps 8 and 9, one THREAD per image: Psi_8 is 4 x 4 ----
+__global__ void __launch_bounds__(128) hw_tail89_kernel(const __grid_constant__ EncodeParams P,
+                                                        const float* __restrict__ ws_in) {
+  const int64_t img = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= P.N) return;
+  const float* psi = ws_in + (size_t)img * kWsStride;  // [4][2*2]
+  float m[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 v = ldg4(psi + 4 * i);
+    m[4 * i] = v.x; m[4 * i + 1] = v.y; m[4 * i + 2] = v.z; m[4 * i + 3] = v.w;
+  }
+  // step 8: M_8[(s,l)][c] = Psi_8[l][2s + c]: two columns of length 8; one rotation orthogonalises them
+  float a[8], b[8];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      a[s * 4 + l] = m[l * 4 + 2 * s];
+      b[s * 4 + l] = m[l * 4 + 2 * s + 1];
+    }
+  float aa = 0.f, bb = 0.f, ab = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    aa = fmaf(a[e], a[e], aa);
+    bb = fmaf(b[e], b[e], bb);
+    ab = fmaf(a[e], b[e], ab);
+  }
+  const float thr2 = kFloor2 * (aa + bb);
+  int sweeps8 = 0;
+  if (aa + bb > 0.f) {
+    sweeps8 = 1;
+    if (ab * ab > kTol2 * aa * bb && aa > thr2 && bb > thr2) {
+      float c, s;
+      jacobi_cs(aa, bb, ab, c, s);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = a[e], y = b[e];
+        a[e] = c * x - s * y;
+        b[e] = s * x + c * y;
+      }
+    }
+    aa = bb = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      aa = fmaf(a[e], a[e], aa);
+      bb = fmaf(b[e], b[e], bb);
+    }
+  }
+  {
+    const Out io = make_out(P, img, 8);
+    const bool afirst = aa >= bb;  // stable descending order
+    const float n0 = afirst ? aa : bb, n1 = afirst ? bb : aa;
+    const bool k0 = n0 > thr2 && 0 < io.r_rt, k1 = n1 > thr2 && 1 < io.r_rt;
+    const float i0 = k0 ? rsqrtf(n0) : 0.f, i1 = k1 ? rsqrtf(n1) : 0.f;
+    float u0[8], u1[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      u0[e] = (afirst ? a[e] : b[e]) * i0;
+      u1[e] = (afirst ? b[e] : a[e]) * i1;
+    }
+    if (io.sv) {
+      for (int k = 0; k < io.sv_width; ++k) io.sv[k] = 0.f;
+      io.sv[0] = n0 > thr2 ? sqrtf(n0) : 0.f;
+      if (io.sv_width > 1) io.sv[1] = n1 > thr2 ? sqrtf(n1) : 0.f;
+    }
+    if (io.sweeps) *io.sweeps = sweeps8;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < io.b_rt) {
+          if (0 < io.r_rt) io.A[(s * io.b_rt + l) * io.r_rt + 0] = u0[s * 4 + l];
+          if (1 < io.r_rt) io.A[(s * io.b_rt + l) * io.r_rt + 1] = u1[s * 4 + l];
+        }
+    // Psi_9[r][c] = sum_e U[e][r] M_8[e][c]
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const float mc0 = m[l * 4 + 2 * s], mc1 = m[l * 4 + 2 * s + 1];
+        p[0] = fmaf(u0[s * 4 + l], mc0, p[0]);
+        p[1] = fmaf(u0[s * 4 + l], mc1, p[1]);
+        p[2] = fmaf(u1[s * 4 + l], mc0, p[2]);
+        p[3] = fmaf(u1[s * 4 + l], mc1, p[3]);
+      }
+    // step 9: M_9[(s,l)] = Psi_9[l][s] (4 x 1) -> A_9 = M / |M|; the 1 x 1 S.V is dropped (unit norm)
+    const Out io9 = make_out(P, img, 9);
+    const float nn = p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3];
+    const float inv = nn > 0.f ? rsqrtf(nn) : 0.f;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int l = 0; l < 2; ++l)
+        if (l < io9.b_rt) io9.A[s * io9.b_rt + l] = p[l * 2 + s] * inv;
+    if (io9.sv) {
+      for (int k = 0; k < io9.sv_width; ++k) io9.sv[k] = 0.f;
+      io9.sv[0] = sqrtf(nn);
+    }
+    if (io9.sweeps) *io9.sweeps = 0;
   }
 }
 
@@ -990,10 +842,9 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
                                 int sms, cudaStream_t st) {
   const int per_cta = kHwWarps * 2;
   const int grid = (int)((P.N + per_cta - 1) / per_cta);
-  const size_t smem_head = (size_t)per_cta * (1024 + ysm_floats(2) + refl_floats(3)) * sizeof(float);
-  const size_t smem3 = (size_t)per_cta * (ysm_floats(3) + refl_floats(1)) * sizeof(float);
-  const size_t smem4 = (size_t)per_cta * (ysm_floats(4) + refl_floats(0)) * sizeof(float);
-  const size_t smem5 = (size_t)per_cta * refl_floats(1) * sizeof(float);
+  const size_t smem_head = (size_t)per_cta * (1024 + ysm_floats(2)) * sizeof(float);
+  const size_t smem3 = (size_t)per_cta * ysm_floats(3) * sizeof(float);
+  const size_t smem4 = (size_t)per_cta * ysm_floats(4) * sizeof(float);
   uint8_t* keys = reinterpret_cast<uint8_t*>(sort_ws);
   int32_t* perm = reinterpret_cast<int32_t*>(keys + ((chunk + 255) & ~(int64_t)255));
   int32_t* bins = perm + chunk + 2 * kSortBins;
@@ -1020,13 +871,16 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
     hw_row_kernel<4, false, false><<<grid, kHwWarps * 32, smem4, st>>>(P, ws1, ws0, nullptr, nullptr, nullptr);
   }
   ee.mark(3, st);
-  hw_col5_kernel<<<grid, kHwWarps * 32, smem5, st>>>(P, ws0, ws1);
+  hw_col_kernel<5><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
   ee.mark(4, st);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  e = launch_steps<32, 6, 10>(P, ws1, nullptr, sms, st);
+  // tail: steps 6 and 7 with 8 / 16 images per warp, steps 8-9 one thread per image
+  const int ipc6 = kHwWarps * ColShape<6>::IPW, ipc7 = kHwWarps * ColShape<7>::IPW;
+  hw_col_kernel<6><<<(int)((P.N + ipc6 - 1) / ipc6), kHwWarps * 32, 0, st>>>(P, ws1, ws0);
+  hw_col_kernel<7><<<(int)((P.N + ipc7 - 1) / ipc7), kHwWarps * 32, 0, st>>>(P, ws0, ws1);
+  hw_tail89_kernel<<<(int)((P.N + 127) / 128), 128, 0, st>>>(P, ws1);
   ee.mark(5, st);
-  return e;
+  (void)sms;
+  return cudaGetLastError();
 }
 
 }  // namespace hw
