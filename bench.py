@@ -3,7 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A step = one pass of the hot path (encode kernel + overlap kernel + count) over
+A step = one pass of the hot path (encode kernels + overlap kernel + count) over
 one batch of synthetic MNIST-shaped images.  Workload at N=1 = BASELINE.json
 configs[1]: the full 60k/10k split (70,000 images, 219.5 MB of fp32 pixels —
 larger than the 126 MB L2, so every step streams its input from HBM).  At N>1
@@ -31,8 +31,9 @@ FLOP_STEP4 = 721_920         # the 32 x 32 SVD step (bond 4 ->
 FLOP_CLASSIFY = 257_456
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
 # (hw_row_kernel<4>, 70,000 images) from `ncu --set full` of this command
-# (profiles/README.md); None until a capture of the current kernel exists
-TRAFFIC_STEP4_BYTES = None
+# (profiles/ncu_step4_r1.csv: 293.03 MB read + 519.70 MB written; algorithmic
+# 3 x 4 KB per image = 860 MB)
+TRAFFIC_STEP4_BYTES = 812_730_880
 BYTES_IMG = 784 * 4 + 16 * 4 + 4
 
 
@@ -311,9 +312,9 @@ def main():
             "e2e_u8": {"value": world * N * args.steps / (e2e_u8_ms * 1e-3), "unit": "images/s",
                        "h2d_bytes_per_step": int(N * 784), "d2h_bytes_per_step": int(N * (16 * 4 + 4)),
                        "host_input": "uint8 pixels (MNIST's native type), pinned; /255 in the encoder load"},
-            # per step: 5 encode kernels (head | step 3 | step 4 | step 5 | tail) per 131,072-image
-            # chunk + overlap prep + overlap + count
-            "gpu_launches": (5 * ((N + 131071) // 131072) + 3) * args.steps,
+            # per step: 11 encode kernels per 131,072-image chunk (head | step 3 | 3 x pairing sort |
+            # step 4 | step 5 | step 6 | step 7 | steps 8-9) + overlap prep + overlap + count
+            "gpu_launches": (11 * ((N + 131071) // 131072) + 3) * args.steps,
             "kernels_ms": {"encode": enc_ms, "overlap": ovl_ms,
                            "encode_launches": dict(zip(["head_0_2", "step3", "step4", "step5", "tail_6_9"],
                                                        launch_ms))},
