@@ -156,6 +156,9 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
