@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=17_500, help="images per H2D/compute pipeline stage")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -236,7 +237,7 @@ def main():
     ov_pin = torch.empty((N, 16), dtype=torch.float32).pin_memory()
     am_pin = torch.empty((N,), dtype=torch.int32).pin_memory()
 
-    pipe = batched.HostPipeline(clf, 784, D_ENCODE, chunk=17_500)
+    pipe = batched.HostPipeline(clf, 784, D_ENCODE, chunk=args.e2e_chunk)
 
     def e2e_step():
         # public host API: pinned images in, |overlaps| + argmax back on the host;
@@ -257,7 +258,7 @@ def main():
     # same, with the pixels as the uint8 MNIST ships (the synthetic images are k/255 exactly);
     # /255 happens in the encoder's load (OC_U8)
     imgs_u8 = torch.from_numpy(np.rint(imgs_h * 255.0).astype(np.uint8)).pin_memory()
-    pipe8 = batched.HostPipeline(clf, 784, D_ENCODE, chunk=17_500, in_dtype=torch.uint8)
+    pipe8 = batched.HostPipeline(clf, 784, D_ENCODE, chunk=args.e2e_chunk, in_dtype=torch.uint8)
     for _ in range(2):
         pipe8.run(imgs_u8, ov_pin, am_pin)
     barrier()
