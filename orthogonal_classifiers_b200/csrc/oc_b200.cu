@@ -16,6 +16,7 @@
 #include "oc_generic.cuh"
 #include "oc_encode_fast.cuh"
 #include "oc_encode_hw.cuh"
+#include "oc_encode_gram.cuh"
 #include "oc_overlap_fast.cuh"
 
 namespace {
@@ -104,6 +105,10 @@ int oc_set_option(const char* key, int value) {
   }
   if (key && !strcmp(key, "enc_sort")) {
     oc::hw::sort_pairs() = value;
+    return OC_OK;
+  }
+  if (key && !strcmp(key, "enc_gram")) {
+    oc::gram::enabled() = value;
     return OC_OK;
   }
   if (key && !strcmp(key, "enc_hw")) {

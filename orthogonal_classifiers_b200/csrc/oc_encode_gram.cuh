@@ -1,0 +1,495 @@
+// Gram-matrix front end of the half-warp encoder: steps 0..3 of the chain for
+// L = 10, D > 16 (no truncation before bond 5), replacing the head (steps 0-2)
+// and step-3 Jacobi kernels of oc_encode_hw.cuh.
+//
+// With X_n the (2^(n+1) x 2^(9-n)) row unfolding of the padded image
+// (tools.py:218-220), step n of the chain is the SVD of
+//   M_n[(s,l), c] = sum_i U^(n-1)[i][l] X_n[2i+s][c],
+// U^(n-1) = left singular vectors of X_{n-1} (an isometry onto the row space,
+// so nothing is lost).  Hence the left singular vectors of M_n are
+//   A_n[(s,l), r] = sum_i U^(n-1)[i][l] U^(n)[2i+s][r],
+// the singular values are those of X_n, and U^(n) are the eigenvectors of the
+// SMALL Gram matrix G_n = X_n X_n^T (2^(n+1) square):
+//   G_3 (16 x 16) is accumulated from the pixels in fp64 (products of fp32
+//   pixels are exact in fp64), G_2, G_1, G_0 are partial traces of it;
+//   G_n = L L^T by diagonally pivoted Cholesky in fp64 (columns in pivot
+//   order, rows in place); one-sided Jacobi on the COLUMNS of L in fp32
+//   (Veselic-Hari: converged columns are U^(n) Sigma^(n) with relative
+//   accuracy, and the pivoting preconditions the iteration: 3.8 sweeps at
+//   n = 3 against 7 on the 16 x 64 rows).
+// The Jacobi vectors are 16 / 8 / 4 / 2 long instead of 64 / 128 / 256 / 512, and
+// the four eigenproblems of an image run side by side in the 16 lanes of its
+// half-warp (lanes 0-7 | 8-11 | 12-13 | 14).  Psi_4 = U^(3)^T X_3 goes to the
+// global workspace for the step-4 kernel, as before.
+#pragma once
+#include "oc_encode_hw.cuh"
+
+namespace oc {
+namespace gram {
+
+using hw::dot16;
+using hw::kHwWarps;
+using hw::make_out;
+using hw::Out;
+using hw::rotate16;
+
+constexpr int kGStride = 256;      // doubles per image in the Gram workspace (G_3, full symmetric)
+constexpr int kXdStride = 66;      // doubles per row of X_3 in shared memory (conflict-free 128-bit reads)
+constexpr double kCholFloor = 1e-13;  // pivots below this fraction of trace(G) end the factorisation
+
+// ---- pixels: four consecutive amplitudes i .. i+3 of the tail-padded image ----
+struct PixRow {
+  const void* p;
+  int dtype, n_pix;
+  bool vec, vec8;
+};
+__device__ __forceinline__ PixRow pix_row(const EncodeParams& P, int64_t img) {
+  PixRow r;
+  const char* src = reinterpret_cast<const char*>(P.images);
+  const int esz = P.in_dtype == 0 ? 4 : (P.in_dtype == 1 ? 8 : 1);
+  r.p = src + (size_t)img * P.ld * esz;
+  r.dtype = P.in_dtype;
+  r.n_pix = P.n_pix;
+  r.vec = P.in_dtype == 0 && ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  r.vec8 = P.in_dtype == 2 && ((P.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+  return r;
+}
+__device__ __forceinline__ float4 pix4(const PixRow& r, int i) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r.vec && i + 3 < r.n_pix) {
+    v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r.p) + i));
+  } else if (r.vec8 && i + 3 < r.n_pix) {
+    const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(r.p) + i));
+    v = make_float4(float(u.x) / 255.f, float(u.y) / 255.f, float(u.z) / 255.f, float(u.w) / 255.f);
+  } else {
+    if (i < r.n_pix) v.x = load_pixel<float>(r.p, r.dtype, i);
+    if (i + 1 < r.n_pix) v.y = load_pixel<float>(r.p, r.dtype, i + 1);
+    if (i + 2 < r.n_pix) v.z = load_pixel<float>(r.p, r.dtype, i + 2);
+    if (i + 3 < r.n_pix) v.w = load_pixel<float>(r.p, r.dtype, i + 3);
+  }
+  return v;
+}
+
+// ---- K1a: G_3 = X_3 X_3^T in fp64, one image per half-warp ----
+// Lane i owns row i and accumulates the pairs (i, (i+t) mod 16), t = 0..8:
+// every unordered pair exactly once (t = 8 twice, same bits).
+__global__ void __launch_bounds__(kHwWarps * 32) gram_kernel(const __grid_constant__ EncodeParams P,
+                                                             double* __restrict__ g_out) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l16 = lane & 15, h = lane >> 4;
+  const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
+  const bool valid = img < P.N;
+  double* Xd = smem_d + (size_t)(warp * 2 + h) * 16 * kXdStride;
+  const PixRow src = pix_row(P, valid ? img : 0);
+#pragma unroll 4
+  for (int i = 4 * l16; i < 1024; i += 64) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) v = pix4(src, i);
+    double* d = Xd + (i >> 6) * kXdStride + (i & 63);
+    *reinterpret_cast<double2*>(d) = make_double2((double)v.x, (double)v.y);
+    *reinterpret_cast<double2*>(d + 2) = make_double2((double)v.z, (double)v.w);
+  }
+  __syncwarp();
+  const int rows_live = (P.n_pix + 63) >> 6;
+  double acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.0;
+  if (l16 < rows_live) {
+    const double* xi = Xd + l16 * kXdStride;
+#pragma unroll 2
+    for (int k = 0; k < 64; k += 2) {
+      const double2 a = *reinterpret_cast<const double2*>(xi + k);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const double2 b = *reinterpret_cast<const double2*>(Xd + ((l16 + t) & 15) * kXdStride + k);
+        acc[t] = fma(a.x, b.x, acc[t]);
+        acc[t] = fma(a.y, b.y, acc[t]);
+      }
+    }
+  }
+  if (valid) {
+    double* g = g_out + (size_t)img * kGStride;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int j = (l16 + t) & 15;
+      g[l16 * 16 + j] = acc[t];
+      g[j * 16 + l16] = acc[t];
+    }
+  }
+}
+
+// ---- shared-memory map of one image in K1b ----
+// Gram matrices, row stride p + 1 (lane = row reads column piv without conflicts)
+__host__ __device__ constexpr int g_off(int n) { return n == 3 ? 0 : (n == 2 ? 272 : (n == 1 ? 344 : 364)); }
+constexpr int kGsDoubles = 372;
+// L rows for the pivot-row broadcast, [row][col], stride p
+__host__ __device__ constexpr int l_off(int n) { return n == 3 ? 0 : (n == 2 ? 256 : (n == 1 ? 320 : 336)); }
+constexpr int kLsDoubles = 340;
+// fp32 L columns [k][row], stride p, for the Jacobi load (offsets l_off)
+constexpr int kLfFloats = 340;
+// After the factorisation the Gram region holds U^(n) as fp32 [rank][row], stride
+// p + 1 (offsets g_off), and the L-row region U^(3) transposed, [row][rank].
+constexpr int kHeadSmemBytes = kGsDoubles * 8 + kLsDoubles * 8 + kLfFloats * 4;  // 7,056 B: 4 CTAs of 8 images per SM
+
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(FULL, lo, src);
+  hi = __shfl_sync(FULL, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
+// Diagonally pivoted Cholesky of the p x p matrix g (row stride p + 1) by the p
+// lanes [gbase, gbase + p) of the warp, lane - gbase = row.  Lanes of different
+// groups (and different p <= KMAX) run side by side; p = 0: idle lane.
+// ls: [row][col] fp64 copy (pivot rows are broadcast through it); lf: fp32
+// [col][row].  Returns the number of columns (the numerical rank).
+template <int KMAX>
+__device__ __forceinline__ int pivoted_cholesky(const double* __restrict__ g, double* __restrict__ ls,
+                                                float* __restrict__ lf, int p, int gbase, int lane,
+                                                double inv_trace) {
+  const int row = lane - gbase;
+  const unsigned gmask = p > 0 ? (((p >= 32 ? 0u : (1u << p)) - 1u) << gbase) : (1u << lane);
+  double lrow[KMAX];
+  double d = (p > 0) ? g[row * (p + 1) + row] : 0.0;
+  bool done = p == 0, fin = p == 0;
+  int rank = 0;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const bool on = k < p && !fin;
+    // pivot = largest remaining diagonal (fp32 key, row index in the low bits; ties -> lowest row)
+    const float dn = (float)(d * inv_trace);
+    unsigned key = 0u;
+    if (on && !done && dn > (float)kCholFloor) key = (__float_as_uint(dn) & ~15u) | (unsigned)(15 - row);
+    const unsigned kmax = __reduce_max_sync(gmask, key);
+    if (kmax == 0u) fin = true;
+    const int piv = 15 - (int)(kmax & 15u);
+    const double dpiv = shfl_d(d, gbase + (piv & (p > 0 ? p - 1 : 0)));
+    double v = 0.0;
+    if (on && !fin) {
+      const double inv = rsqrt(dpiv);
+      double dotv = 0.0;
+      const double* lp = ls + piv * p;
+#pragma unroll
+      for (int j = 0; j + 1 < k; j += 2) {
+        const double2 b = *reinterpret_cast<const double2*>(lp + j);
+        dotv = fma(lrow[j], b.x, dotv);
+        dotv = fma(lrow[j + 1], b.y, dotv);
+      }
+      if (k & 1) dotv = fma(lrow[k - 1], lp[k - 1], dotv);
+      v = (g[row * (p + 1) + piv] - dotv) * inv;
+      if (row == piv) v = dpiv * inv;
+      if (done) v = 0.0;
+      ++rank;
+    }
+    lrow[k] = v;
+    if (k < p) {
+      ls[row * p + k] = v;
+      lf[k * p + row] = (float)v;
+    }
+    d = fma(-v, v, d);
+    if (on && !fin && row == piv) done = true;
+    __syncwarp();
+  }
+  return rank;
+}
+
+// One-sided Jacobi (odd-even ordering) on the 2 * gsz vectors of each lane
+// group [gbase, gbase + gsz), 16 elements per vector, groups of different size
+// side by side.  Same rotation kernel and stopping rule as hw::jacobi16.
+__device__ __forceinline__ int jacobi_groups(u64 (&T)[16], u64 (&S)[16], float& nT, float& nS, float thr2,
+                                             int lane, int gsz, int gbase, int mlive, int mlive_max) {
+  const int slot = lane - gbase;
+  const int src_dn = gbase + ((slot + 1) & (gsz - 1));
+  const int src_up = gbase + ((slot - 1) & (gsz - 1));
+  const bool idleB = slot >= mlive - 1;
+  const unsigned gmask = ((1u << gsz) - 1u) << gbase;
+  int sweeps = 0;
+  bool done = mlive == 0;
+#pragma unroll 1
+  for (int sw = 0; sw < kMaxSweeps; ++sw) {
+    bool again = false;
+    bool lostf = false;
+    {
+      const float fT = dot16<0, 8>(T, T), fS = dot16<0, 8>(S, S);
+      if (!done) {
+        nT = fT;
+        nS = fS;
+      }
+    }
+#pragma unroll 1
+    for (int rr = 0; rr < mlive_max; ++rr) {
+      const bool off = done || rr >= mlive;
+      rotate16<0, 8>(T, S, nT, nS, thr2, off, lostf, again);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) T[e] = shfl2(T[e], src_dn);
+      float nR = __shfl_sync(FULL, nT, src_dn);
+      rotate16<0, 8>(S, T, nS, nR, thr2, off || idleB, lostf, again);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) T[e] = shfl2(T[e], src_up);
+      nT = __shfl_sync(FULL, nR, src_up);
+      {
+        const unsigned lostmask = __ballot_sync(FULL, lostf);
+        if (lostmask) {
+          const float fT = dot16<0, 8>(T, T), fS = dot16<0, 8>(S, S);
+          if (lostmask & gmask) {
+            nT = fT;
+            nS = fS;
+          }
+          lostf = false;
+        }
+      }
+    }
+    if (!done) ++sweeps;
+    const unsigned b = __ballot_sync(FULL, again);
+    if (mlive <= 1 || !(b & gmask)) done = true;
+    if (__all_sync(FULL, done)) break;
+  }
+  return sweeps;
+}
+
+// ---- K1b: steps 0..3 from G_3; Psi_4 to the workspace ----
+__global__ void __launch_bounds__(kHwWarps * 32, 4)
+gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restrict__ g_in,
+                 float* __restrict__ ws_out, uint8_t* __restrict__ keys) {
+  extern __shared__ __align__(16) unsigned char smem_b[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l16 = lane & 15, hb = lane & 16, h = lane >> 4;
+  const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
+  const bool valid = img < P.N;
+  const int64_t im = valid ? img : 0;
+  unsigned char* mine = smem_b + (size_t)(warp * 2 + h) * kHeadSmemBytes;
+  double* Gs = reinterpret_cast<double*>(mine);
+  double* Ls = Gs + kGsDoubles;
+  float* Lf = reinterpret_cast<float*>(Ls + kLsDoubles);
+  float* Uf = reinterpret_cast<float*>(Gs);  // after the factorisation
+  float* Ut = reinterpret_cast<float*>(Ls);  // after the factorisation
+
+  // ---- G_3 -> shared (row stride 17), partial traces G_2, G_1, G_0 ----
+  {
+    const double* g = g_in + (size_t)im * kGStride;
+#pragma unroll 4
+    for (int e = l16; e < 256; e += 16) Gs[(e >> 4) * 17 + (e & 15)] = valid ? __ldg(g + e) : 0.0;
+  }
+  __syncwarp();
+  double tr = Gs[l16 * 17 + l16];
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) tr += shfl_d(tr, lane ^ o);
+  const double inv_trace = tr > 0.0 ? 1.0 / tr : 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = l16 + 16 * q, i = e >> 3, j = e & 7;
+    Gs[g_off(2) + i * 9 + j] = Gs[(2 * i) * 17 + 2 * j] + Gs[(2 * i + 1) * 17 + 2 * j + 1];
+  }
+  __syncwarp();
+  {
+    const int i = l16 >> 2, j = l16 & 3;
+    Gs[g_off(1) + i * 5 + j] =
+        Gs[g_off(2) + (2 * i) * 9 + 2 * j] + Gs[g_off(2) + (2 * i + 1) * 9 + 2 * j + 1];
+  }
+  __syncwarp();
+  if (l16 < 4) {
+    const int i = l16 >> 1, j = l16 & 1;
+    Gs[g_off(0) + i * 3 + j] =
+        Gs[g_off(1) + (2 * i) * 5 + 2 * j] + Gs[g_off(1) + (2 * i + 1) * 5 + 2 * j + 1];
+  }
+  __syncwarp();
+
+  // ---- pivoted Cholesky: problem 3 on all 16 lanes, then 2 | 1 | 0 side by side ----
+  const int rank3 = pivoted_cholesky<16>(Gs, Ls, Lf, 16, hb, lane, inv_trace);
+  // small problems: lanes 0-7 -> n = 2, 8-11 -> n = 1, 12-13 -> n = 0, 14-15 idle
+  const int nS_ = l16 < 8 ? 2 : (l16 < 12 ? 1 : 0);
+  const int pS_ = l16 < 8 ? 8 : (l16 < 12 ? 4 : (l16 < 14 ? 2 : 0));
+  const int bS_ = hb + (l16 < 8 ? 0 : (l16 < 12 ? 8 : (l16 < 14 ? 12 : l16)));
+  const int rankS = pivoted_cholesky<8>(Gs + g_off(nS_), Ls + l_off(nS_), Lf + l_off(nS_), pS_, bS_, lane,
+                                        inv_trace);
+  const int rank2 = __shfl_sync(FULL, rankS, hb + 0);
+  const int rank1 = __shfl_sync(FULL, rankS, hb + 8);
+  const int rank0 = __shfl_sync(FULL, rankS, hb + 12);
+
+  // ---- Jacobi on the columns of L_n: lanes 0-7 -> n = 3 (8 slots), 8-11 -> 2, 12-13 -> 1, 14 -> 0 ----
+  const int nJ = l16 < 8 ? 3 : (l16 < 12 ? 2 : (l16 < 14 ? 1 : 0));
+  const int gsz = l16 < 8 ? 8 : (l16 < 12 ? 4 : (l16 < 14 ? 2 : 1));
+  const int gb16 = l16 < 8 ? 0 : (l16 < 12 ? 8 : (l16 < 14 ? 12 : l16));
+  const int gbase = hb + gb16;
+  const int slot = l16 - gb16;
+  const int pJ = 2 * gsz;  // matrix size of this lane's problem
+  const int rankJ = l16 == 15 ? 0 : (nJ == 3 ? rank3 : (nJ == 2 ? rank2 : (nJ == 1 ? rank1 : rank0)));
+  u64 T[16], S[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) T[e] = S[e] = 0ull;
+  {
+    const float* lt = Lf + l_off(nJ) + (2 * slot) * pJ;
+    const float* lsn = lt + pJ;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (2 * e < pJ && l16 != 15) {
+        const float2 a = *reinterpret_cast<const float2*>(lt + 2 * e);
+        const float2 b = *reinterpret_cast<const float2*>(lsn + 2 * e);
+        T[e] = pack2(a.x, a.y);
+        S[e] = pack2(b.x, b.y);
+      }
+    }
+  }
+  __syncwarp();
+  float nT = dot16<0, 8>(T, T), nS = dot16<0, 8>(S, S);
+  float fro = nT + nS;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    const float v = __shfl_xor_sync(FULL, fro, o);
+    if (o < gsz) fro += v;
+  }
+  const float thr2 = kFloor2 * fro;
+  const int mlive = (rankJ + 1) >> 1;
+  int mlive_max = mlive;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mlive_max = max(mlive_max, __shfl_xor_sync(FULL, mlive_max, o));
+  int sweeps = 0;
+  if (mlive_max > 0) {
+    sweeps = jacobi_groups(T, S, nT, nS, thr2, lane, gsz, gbase, mlive, mlive_max);
+    nT = dot16<0, 8>(T, T);
+    nS = dot16<0, 8>(S, S);
+  }
+  // stable descending rank among the 2 * gsz vectors of the group
+  int rT = 0, rS = 0;
+  {
+    const int pT = 2 * slot, pS = pT + 1;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float v = __shfl_sync(FULL, (j & 1) ? nS : nT, gbase + ((j >> 1) & (gsz - 1)));
+      if (j < pJ) {
+        rT += (v > nT) || (v == nT && j < pT);
+        rS += (v > nS) || (v == nS && j < pS);
+      }
+    }
+  }
+  const Out io = make_out(P, im, nJ);
+  const int r_rt = io.r_rt;
+  const bool aT = nT > thr2 && l16 != 15, aS = nS > thr2 && l16 != 15;
+  const bool kT = aT && rT < r_rt, kS = aS && rS < r_rt;
+  if (valid && l16 != 15) {
+    if (io.sv) {
+      if (rT < io.sv_width) io.sv[rT] = aT ? sqrtf(nT) : 0.f;
+      if (rS < io.sv_width) io.sv[rS] = aS ? sqrtf(nS) : 0.f;
+      for (int k = pJ + slot; k < io.sv_width; k += gsz) io.sv[k] = 0.f;
+    }
+    if (io.sweeps && slot == 0) *io.sweeps = sweeps;
+  }
+  {
+    // kept vectors of problem 3 = non-zero rows of Psi_4 (pairing key of step 4)
+    const unsigned kt = __ballot_sync(FULL, kT && nJ == 3), ks = __ballot_sync(FULL, kS && nJ == 3);
+    const int kept = __popc((kt >> hb) & 0xffu) + __popc((ks >> hb) & 0xffu);
+    if (keys && valid && l16 == 0) keys[im] = (uint8_t)kept;
+  }
+  // ---- U^(n)[row][rank] -> shared: Uf [rank][row] (stride p + 1); U^(3) also transposed ----
+  if (l16 != 15) {
+    const float iT = kT ? rsqrtf(nT) : 0.f, iS = kS ? rsqrtf(nS) : 0.f;
+    float* uT = Uf + g_off(nJ) + rT * (pJ + 1);
+    float* uS = Uf + g_off(nJ) + rS * (pJ + 1);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (2 * e < pJ) {
+        float t0, t1, s0, s1;
+        unpack2(T[e], t0, t1);
+        unpack2(S[e], s0, s1);
+        t0 *= iT; t1 *= iT; s0 *= iS; s1 *= iS;
+        uT[2 * e] = t0; uT[2 * e + 1] = t1;
+        uS[2 * e] = s0; uS[2 * e + 1] = s1;
+        if (nJ == 3) {
+          Ut[(2 * e) * 16 + rT] = t0; Ut[(2 * e + 1) * 16 + rT] = t1;
+          Ut[(2 * e) * 16 + rS] = s0; Ut[(2 * e + 1) * 16 + rS] = s1;
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- A_n[(s,l), r] = sum_i U^(n-1)[i][l] U^(n)[2i+s][r] ----
+  if (valid) {
+    float* mps = reinterpret_cast<float*>(P.mps_out) + (size_t)im * P.mps_stride;
+    {
+      float* A0 = mps + P.site_off[0];
+      const int r0 = P.bonds[1];
+      if (l16 < 4) {
+        const int s = l16 >> 1, r = l16 & 1;
+        if (r < r0) A0[s * r0 + r] = Uf[g_off(0) + r * 3 + s];
+      }
+    }
+#pragma unroll 1
+    for (int n = 1; n <= 3; ++n) {
+      const int b = 1 << n, p = 2 * b;
+      float* A = mps + P.site_off[n];
+      const int b_rt = P.bonds[n], rr_rt = P.bonds[n + 1];
+      const float* up = Uf + g_off(n - 1);  // [l][i], stride b + 1
+      const float* un = Uf + g_off(n);      // [r][row], stride p + 1
+      for (int o = l16; o < 2 * b * p; o += 16) {
+        const int r = o & (p - 1), l = (o >> (n + 1)) & (b - 1), s = o >> (2 * n + 1);
+        float acc = 0.f;
+        for (int i = 0; i < b; ++i) acc = fmaf(up[l * (b + 1) + i], un[r * (p + 1) + 2 * i + s], acc);
+        if (l < b_rt && r < rr_rt) A[(s * b_rt + l) * rr_rt + r] = acc;
+      }
+    }
+  }
+
+  // ---- Psi_4[l][c] = sum_i U^(3)[i][l] X_3[i][c]; this lane: c = 4 l16 .. 4 l16 + 3, all l ----
+  {
+    const PixRow src = pix_row(P, im);
+    const int rows_live = (P.n_pix + 63) >> 6;
+    float acc[16][4];
+#pragma unroll
+    for (int l = 0; l < 16; ++l)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[l][q] = 0.f;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && rows_live > 0) x = pix4(src, 4 * l16);
+#pragma unroll 1
+    for (int i = 0; i < rows_live; ++i) {
+      const float4 xc = x;
+      if (valid && i + 1 < rows_live) x = pix4(src, 64 * (i + 1) + 4 * l16);
+      const float xv[4] = {xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+      for (int l4 = 0; l4 < 4; ++l4) {
+        const float4 u = *reinterpret_cast<const float4*>(Ut + i * 16 + 4 * l4);
+        const float uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[4 * l4 + a][q] = fmaf(uv[a], xv[q], acc[4 * l4 + a][q]);
+      }
+    }
+    if (valid) {
+      float* out = ws_out + (size_t)im * kWsStride + 4 * l16;
+#pragma unroll
+      for (int l = 0; l < 16; ++l)
+        *reinterpret_cast<float4*>(out + l * 64) = make_float4(acc[l][0], acc[l][1], acc[l][2], acc[l][3]);
+    }
+  }
+}
+
+inline int& enabled() {
+  static int v = 1;
+  return v;
+}
+
+// steps 0..3: images -> A_0..A_3, Psi_4 (ws_psi4), keys (nullable); gws: kGStride doubles per image
+inline cudaError_t launch_head(const EncodeParams& P, double* gws, float* ws_psi4, uint8_t* keys,
+                               cudaStream_t st) {
+  const int per_cta = kHwWarps * 2;
+  const int grid = (int)((P.N + per_cta - 1) / per_cta);
+  const size_t smem_a = (size_t)per_cta * 16 * kXdStride * sizeof(double);
+  const size_t smem_b = (size_t)per_cta * kHeadSmemBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gram_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  gram_kernel<<<grid, kHwWarps * 32, smem_a, st>>>(P, gws);
+  gram_head_kernel<<<grid, kHwWarps * 32, smem_b, st>>>(P, gws, ws_psi4, keys);
+  return cudaGetLastError();
+}
+
+}  // namespace gram
+}  // namespace oc

@@ -833,6 +833,13 @@ __global__ void __launch_bounds__(128) hw_tail89_kernel(const __grid_constant__ 
 
 inline bool supported(const EncodeParams& P) { return P.L == 10 && P.D > 16; }
 
+}  // namespace hw
+namespace gram {  // oc_encode_gram.cuh: steps 0..3 from the 16 x 16 Gram matrix
+inline int& enabled();
+inline cudaError_t launch_head(const EncodeParams& P, double* gws, float* ws_psi4, uint8_t* keys, cudaStream_t st);
+}  // namespace gram
+namespace hw {
+
 // steps 0..5 with the half-warp kernels, 6..9 with the v3 tail
 inline int& sort_pairs() {
   static int v = 1;
@@ -851,12 +858,19 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
   const bool sorted = sort_pairs() != 0;
   EncodeEvents& ee = encode_events();
   ee.mark(0, st);
-  hw_head_kernel<<<grid, kHwWarps * 32, smem_head, st>>>(P, ws0);
-  ee.mark(1, st);
-  if (sorted)
-    hw_row_kernel<3, false, true><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1, nullptr, nullptr, keys);
-  else
-    hw_row_kernel<3, false, false><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1, nullptr, nullptr, nullptr);
+  if (gram::enabled()) {
+    // steps 0..3 from the Gram matrix; G_3 (2 KB / image) borrows ws0, which step 4 overwrites later
+    const cudaError_t e = gram::launch_head(P, reinterpret_cast<double*>(ws0), ws1, sorted ? keys : nullptr, st);
+    if (e != cudaSuccess) return e;
+    ee.mark(1, st);
+  } else {
+    hw_head_kernel<<<grid, kHwWarps * 32, smem_head, st>>>(P, ws0);
+    ee.mark(1, st);
+    if (sorted)
+      hw_row_kernel<3, false, true><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1, nullptr, nullptr, keys);
+    else
+      hw_row_kernel<3, false, false><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1, nullptr, nullptr, nullptr);
+  }
   ee.mark(2, st);
   if (sorted) {
     // step 4 costs (live rows) x (sweeps) per WARP: pair images with equal numbers of live rows
