@@ -22,6 +22,7 @@
 // half-warp (lanes 0-7 | 8-11 | 12-13 | 14).  Psi_4 = U^(3)^T X_3 goes to the
 // global workspace for the step-4 kernel, as before.
 #pragma once
+#include <type_traits>
 #include "oc_encode_hw.cuh"
 
 namespace oc {
@@ -34,7 +35,6 @@ using hw::Out;
 using hw::rotate16;
 
 constexpr int kGStride = 256;      // doubles per image in the Gram workspace (G_3, full symmetric)
-constexpr int kXdStride = 66;      // doubles per row of X_3 in shared memory (conflict-free 128-bit reads)
 constexpr double kCholFloor = 1e-13;  // pivots below this fraction of trace(G) end the factorisation
 
 // ---- pixels: four consecutive amplitudes i .. i+3 of the tail-padded image ----
@@ -70,52 +70,143 @@ __device__ __forceinline__ float4 pix4(const PixRow& r, int i) {
   return v;
 }
 
+// MODE 0: fp32 rows, 16-byte aligned quads, n_pix % 4 == 0 -> one predicated LDG.128, no branches
+// (so that the loads of a whole image can be in flight together); MODE 2: the same for u8;
+// MODE -1: anything else (per-pixel loads).
+template <int MODE>
+__device__ __forceinline__ float4 pix4m(const PixRow& r, int i) {
+  if constexpr (MODE == 0) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < r.n_pix) v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r.p) + i));
+    return v;
+  } else if constexpr (MODE == 2) {
+    uchar4 u = make_uchar4(0, 0, 0, 0);
+    if (i < r.n_pix) u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(r.p) + i));
+    return make_float4(float(u.x) / 255.f, float(u.y) / 255.f, float(u.z) / 255.f, float(u.w) / 255.f);
+  } else {
+    return pix4(r, i);
+  }
+}
+inline int pix_mode(const EncodeParams& P) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(P.images);
+  if ((P.ld & 3) || (P.n_pix & 3)) return -1;
+  if (P.in_dtype == 0 && (a & 15) == 0) return 0;
+  if (P.in_dtype == 2 && (a & 3) == 0) return 2;
+  return -1;
+}
+
 // ---- K1a: G_3 = X_3 X_3^T in fp64, one image per half-warp ----
-// Lane i owns row i and accumulates the pairs (i, (i+t) mod 16), t = 0..8:
-// every unordered pair exactly once (t = 8 twice, same bits).
-__global__ void __launch_bounds__(kHwWarps * 32) gram_kernel(const __grid_constant__ EncodeParams P,
-                                                             double* __restrict__ g_out) {
+// X_3 sits in shared memory k-major, Xt[k][row], as fp64.  Lane = (ia, kq): the
+// 4-row block ia of G against the blocks ia, ia+1, ia+2 (mod 4) - every block
+// pair once, the (ia, ia+2) ones twice - over the k-quarter kq; 48 DFMA per six
+// 128-bit shared loads.  The four k-quarters are then summed with shuffles.
+constexpr int kXtRow = 18;                    // doubles per k (16 rows + pad: 2-way conflicts at most when staging)
+constexpr int kXtQuarter = 16 * kXtRow + 2;  // doubles per k-quarter: the +16 B skew keeps the two
+                                             // k-quarters of a quarter-warp on different banks
+constexpr int kXtDoubles = 4 * kXtQuarter;
+
+__device__ __forceinline__ double shfl_xor_d(double v, int o) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(FULL, lo, o);
+  hi = __shfl_xor_sync(FULL, hi, o);
+  return __hiloint2double(hi, lo);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kHwWarps * 32, 3) gram_kernel(const __grid_constant__ EncodeParams P,
+                                                                double* __restrict__ g_out) {
   extern __shared__ __align__(16) double smem_d[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l16 = lane & 15, h = lane >> 4;
   const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
   const bool valid = img < P.N;
-  double* Xd = smem_d + (size_t)(warp * 2 + h) * 16 * kXdStride;
-  const PixRow src = pix_row(P, valid ? img : 0);
-#pragma unroll 4
-  for (int i = 4 * l16; i < 1024; i += 64) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) v = pix4(src, i);
-    double* d = Xd + (i >> 6) * kXdStride + (i & 63);
-    *reinterpret_cast<double2*>(d) = make_double2((double)v.x, (double)v.y);
-    *reinterpret_cast<double2*>(d + 2) = make_double2((double)v.z, (double)v.w);
+  double* Xt = smem_d + (size_t)(warp * 2 + h) * kXtDoubles;
+  // stage: coalesced loads (all 16 in flight), then fp64 stores Xt[k][row]
+  {
+    const PixRow src = pix_row(P, valid ? img : 0);
+    float4 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) v[r] = pix4m<MODE>(src, 64 * r + 4 * l16);
+    }
+    // keep all 16 loads ahead of the first conversion (the compiler otherwise converts, i.e. waits,
+    // right behind every load)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) asm volatile("" : "+f"(v[r].x), "+f"(v[r].y), "+f"(v[r].z), "+f"(v[r].w));
+    const int k = 4 * l16;
+    double* d = Xt + (k >> 4) * kXtQuarter + (k & 15) * kXtRow;
+#pragma unroll
+    for (int r = 0; r < 16; r += 2) {
+      *reinterpret_cast<double2*>(d + r) = make_double2((double)v[r].x, (double)v[r + 1].x);
+      *reinterpret_cast<double2*>(d + kXtRow + r) = make_double2((double)v[r].y, (double)v[r + 1].y);
+      *reinterpret_cast<double2*>(d + 2 * kXtRow + r) = make_double2((double)v[r].z, (double)v[r + 1].z);
+      *reinterpret_cast<double2*>(d + 3 * kXtRow + r) = make_double2((double)v[r].w, (double)v[r + 1].w);
+    }
   }
   __syncwarp();
-  const int rows_live = (P.n_pix + 63) >> 6;
-  double acc[9];
+  const int ia = l16 & 3, kq = l16 >> 2;
+  const int ib1 = (ia + 1) & 3, ib2 = (ia + 2) & 3;
+  double acc0[4][4], acc1[4][4], acc2[4][4];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = 0.0;
-  if (l16 < rows_live) {
-    const double* xi = Xd + l16 * kXdStride;
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc0[a][b] = acc1[a][b] = acc2[a][b] = 0.0;
+  const double* base = Xt + kq * kXtQuarter;
 #pragma unroll 2
-    for (int k = 0; k < 64; k += 2) {
-      const double2 a = *reinterpret_cast<const double2*>(xi + k);
+  for (int kk = 0; kk < 16; ++kk) {
+    const double* row = base + kk * kXtRow;
+    const double2 a01 = *reinterpret_cast<const double2*>(row + 4 * ia);
+    const double2 a23 = *reinterpret_cast<const double2*>(row + 4 * ia + 2);
+    const double2 b01 = *reinterpret_cast<const double2*>(row + 4 * ib1);
+    const double2 b23 = *reinterpret_cast<const double2*>(row + 4 * ib1 + 2);
+    const double2 c01 = *reinterpret_cast<const double2*>(row + 4 * ib2);
+    const double2 c23 = *reinterpret_cast<const double2*>(row + 4 * ib2 + 2);
+    const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+    const double cv[4] = {c01.x, c01.y, c23.x, c23.y};
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const double2 b = *reinterpret_cast<const double2*>(Xd + ((l16 + t) & 15) * kXdStride + k);
-        acc[t] = fma(a.x, b.x, acc[t]);
-        acc[t] = fma(a.y, b.y, acc[t]);
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b <= a) acc0[a][b] = fma(av[a], av[b], acc0[a][b]);
+        acc1[a][b] = fma(av[a], bv[b], acc1[a][b]);
+        acc2[a][b] = fma(av[a], cv[b], acc2[a][b]);
       }
-    }
   }
+  // sum over the four k-quarters (lanes l16 ^ 4, l16 ^ 8)
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (b <= a) {
+        acc0[a][b] += shfl_xor_d(acc0[a][b], 4);
+        acc0[a][b] += shfl_xor_d(acc0[a][b], 8);
+      }
+      acc1[a][b] += shfl_xor_d(acc1[a][b], 4);
+      acc1[a][b] += shfl_xor_d(acc1[a][b], 8);
+      acc2[a][b] += shfl_xor_d(acc2[a][b], 4);
+      acc2[a][b] += shfl_xor_d(acc2[a][b], 8);
+    }
   if (valid) {
     double* g = g_out + (size_t)img * kGStride;
+    // kq = 0 writes the diagonal block, 1 the (ia, ia+1) block and its mirror, 2 the (ia, ia+2) one
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int j = (l16 + t) & 15;
-      g[l16 * 16 + j] = acc[t];
-      g[j * 16 + l16] = acc[t];
-    }
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int ra = 4 * ia + a;
+        if (kq == 0 && b <= a) {
+          g[ra * 16 + 4 * ia + b] = acc0[a][b];
+          g[(4 * ia + b) * 16 + ra] = acc0[a][b];
+        } else if (kq == 1) {
+          g[ra * 16 + 4 * ib1 + b] = acc1[a][b];
+          g[(4 * ib1 + b) * 16 + ra] = acc1[a][b];
+        } else if (kq == 2) {
+          g[ra * 16 + 4 * ib2 + b] = acc2[a][b];
+          g[(4 * ib2 + b) * 16 + ra] = acc2[a][b];
+        }
+      }
   }
 }
 
@@ -149,7 +240,6 @@ __device__ __forceinline__ int pivoted_cholesky(const double* __restrict__ g, do
                                                 float* __restrict__ lf, int p, int gbase, int lane,
                                                 double inv_trace) {
   const int row = lane - gbase;
-  const unsigned gmask = p > 0 ? (((p >= 32 ? 0u : (1u << p)) - 1u) << gbase) : (1u << lane);
   double lrow[KMAX];
   double d = (p > 0) ? g[row * (p + 1) + row] : 0.0;
   bool done = p == 0, fin = p == 0;
@@ -161,7 +251,12 @@ __device__ __forceinline__ int pivoted_cholesky(const double* __restrict__ g, do
     const float dn = (float)(d * inv_trace);
     unsigned key = 0u;
     if (on && !done && dn > (float)kCholFloor) key = (__float_as_uint(dn) & ~15u) | (unsigned)(15 - row);
-    const unsigned kmax = __reduce_max_sync(gmask, key);
+    unsigned kmax = key;
+#pragma unroll
+    for (int o = KMAX / 2; o > 0; o >>= 1) {
+      const unsigned other = __shfl_xor_sync(FULL, kmax, o);
+      if (o < p) kmax = max(kmax, other);
+    }
     if (kmax == 0u) fin = true;
     const int piv = 15 - (int)(kmax & 15u);
     const double dpiv = shfl_d(d, gbase + (piv & (p > 0 ? p - 1 : 0)));
@@ -249,6 +344,7 @@ __device__ __forceinline__ int jacobi_groups(u64 (&T)[16], u64 (&S)[16], float& 
 }
 
 // ---- K1b: steps 0..3 from G_3; Psi_4 to the workspace ----
+template <int MODE>
 __global__ void __launch_bounds__(kHwWarps * 32, 4)
 gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restrict__ g_in,
                  float* __restrict__ ws_out, uint8_t* __restrict__ keys) {
@@ -268,7 +364,7 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
   // ---- G_3 -> shared (row stride 17), partial traces G_2, G_1, G_0 ----
   {
     const double* g = g_in + (size_t)im * kGStride;
-#pragma unroll 4
+#pragma unroll
     for (int e = l16; e < 256; e += 16) Gs[(e >> 4) * 17 + (e & 15)] = valid ? __ldg(g + e) : 0.0;
   }
   __syncwarp();
@@ -404,58 +500,92 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
   }
   __syncwarp();
 
-  // ---- A_n[(s,l), r] = sum_i U^(n-1)[i][l] U^(n)[2i+s][r] ----
+  // first rows of X_3 for the Psi_4 product: in flight during the A_n products
+  const PixRow src = pix_row(P, im);
+  const int rows_live = (P.n_pix + 63) >> 6;
+  float4 xa[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && j < rows_live) xa[j] = pix4m<MODE>(src, 64 * j + 4 * l16);
+  }
+
+  // ---- A_n[(s,l), r] = sum_i U^(n-1)[i][l] U^(n)[2i+s][r]  (D > 16: natural bonds 2^n) ----
   if (valid) {
     float* mps = reinterpret_cast<float*>(P.mps_out) + (size_t)im * P.mps_stride;
-    {
-      float* A0 = mps + P.site_off[0];
-      const int r0 = P.bonds[1];
-      if (l16 < 4) {
-        const int s = l16 >> 1, r = l16 & 1;
-        if (r < r0) A0[s * r0 + r] = Uf[g_off(0) + r * 3 + s];
+    if (l16 < 4) {  // n = 0: A_0[(s,0), r] = U^(0)[s][r]
+      const int s = l16 >> 1, r = l16 & 1;
+      mps[P.site_off[0] + s * 2 + r] = Uf[g_off(0) + r * 3 + s];
+    }
+    {  // n = 1: one output per lane, (s, l, r) = (bit 3, bit 2, bits 1-0)
+      const int r = l16 & 3, l = (l16 >> 2) & 1, s = l16 >> 3;
+      const float* up = Uf + g_off(0) + l * 3;
+      const float* un = Uf + g_off(1) + r * 5 + s;
+      mps[P.site_off[1] + (s * 2 + l) * 4 + r] = fmaf(up[0], un[0], up[1] * un[2]);
+    }
+    {  // n = 2: lane = (s, r), four l each
+      const int r = l16 & 7, s = l16 >> 3;
+      const float* un = Uf + g_off(2) + r * 9 + s;
+      const float c0 = un[0], c1 = un[2], c2 = un[4], c3 = un[6];
+      float* A = mps + P.site_off[2] + (s * 4) * 8 + r;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const float* up = Uf + g_off(1) + l * 5;
+        A[l * 8] = fmaf(up[0], c0, fmaf(up[1], c1, fmaf(up[2], c2, up[3] * c3)));
       }
     }
-#pragma unroll 1
-    for (int n = 1; n <= 3; ++n) {
-      const int b = 1 << n, p = 2 * b;
-      float* A = mps + P.site_off[n];
-      const int b_rt = P.bonds[n], rr_rt = P.bonds[n + 1];
-      const float* up = Uf + g_off(n - 1);  // [l][i], stride b + 1
-      const float* un = Uf + g_off(n);      // [r][row], stride p + 1
-      for (int o = l16; o < 2 * b * p; o += 16) {
-        const int r = o & (p - 1), l = (o >> (n + 1)) & (b - 1), s = o >> (2 * n + 1);
-        float acc = 0.f;
-        for (int i = 0; i < b; ++i) acc = fmaf(up[l * (b + 1) + i], un[r * (p + 1) + 2 * i + s], acc);
-        if (l < b_rt && r < rr_rt) A[(s * b_rt + l) * rr_rt + r] = acc;
+    {  // n = 3: lane = r, all (s, l)
+      const float* un = Uf + g_off(3) + l16 * 17;
+      float col[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) col[j] = un[j];
+      float* A = mps + P.site_off[3] + l16;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const float* up = Uf + g_off(2) + l * 9;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float u = up[i];
+          a0 = fmaf(u, col[2 * i], a0);
+          a1 = fmaf(u, col[2 * i + 1], a1);
+        }
+        A[l * 16] = a0;
+        A[(8 + l) * 16] = a1;
       }
     }
   }
 
   // ---- Psi_4[l][c] = sum_i U^(3)[i][l] X_3[i][c]; this lane: c = 4 l16 .. 4 l16 + 3, all l ----
   {
-    const PixRow src = pix_row(P, im);
-    const int rows_live = (P.n_pix + 63) >> 6;
     float acc[16][4];
 #pragma unroll
     for (int l = 0; l < 16; ++l)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[l][q] = 0.f;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid && rows_live > 0) x = pix4(src, 4 * l16);
 #pragma unroll 1
-    for (int i = 0; i < rows_live; ++i) {
-      const float4 xc = x;
-      if (valid && i + 1 < rows_live) x = pix4(src, 64 * (i + 1) + 4 * l16);
-      const float xv[4] = {xc.x, xc.y, xc.z, xc.w};
+    for (int i0 = 0; i0 < rows_live; i0 += 4) {
+      float4 xb[4];
 #pragma unroll
-      for (int l4 = 0; l4 < 4; ++l4) {
-        const float4 u = *reinterpret_cast<const float4*>(Ut + i * 16 + 4 * l4);
-        const float uv[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc[4 * l4 + a][q] = fmaf(uv[a], xv[q], acc[4 * l4 + a][q]);
+      for (int j = 0; j < 4; ++j) {
+        xb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && i0 + 4 + j < rows_live) xb[j] = pix4m<MODE>(src, 64 * (i0 + 4 + j) + 4 * l16);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xv[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
+#pragma unroll
+        for (int l4 = 0; l4 < 4; ++l4) {
+          const float4 u = *reinterpret_cast<const float4*>(Ut + (i0 + j) * 16 + 4 * l4);
+          const float uv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[4 * l4 + a][q] = fmaf(uv[a], xv[q], acc[4 * l4 + a][q]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xa[j] = xb[j];
     }
     if (valid) {
       float* out = ws_out + (size_t)im * kWsStride + 4 * l16;
@@ -476,19 +606,26 @@ inline cudaError_t launch_head(const EncodeParams& P, double* gws, float* ws_psi
                                cudaStream_t st) {
   const int per_cta = kHwWarps * 2;
   const int grid = (int)((P.N + per_cta - 1) / per_cta);
-  const size_t smem_a = (size_t)per_cta * 16 * kXdStride * sizeof(double);
+  const size_t smem_a = (size_t)per_cta * kXtDoubles * sizeof(double);
   const size_t smem_b = (size_t)per_cta * kHeadSmemBytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gram_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  gram_kernel<<<grid, kHwWarps * 32, smem_a, st>>>(P, gws);
-  gram_head_kernel<<<grid, kHwWarps * 32, smem_b, st>>>(P, gws, ws_psi4, keys);
-  return cudaGetLastError();
+  const int mode = pix_mode(P);
+  auto launch = [&](auto mode_tag) -> cudaError_t {
+    constexpr int MODE = decltype(mode_tag)::value;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gram_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(gram_head_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    gram_kernel<MODE><<<grid, kHwWarps * 32, smem_a, st>>>(P, gws);
+    gram_head_kernel<MODE><<<grid, kHwWarps * 32, smem_b, st>>>(P, gws, ws_psi4, keys);
+    return cudaGetLastError();
+  };
+  if (mode == 0) return launch(std::integral_constant<int, 0>{});
+  if (mode == 2) return launch(std::integral_constant<int, 2>{});
+  return launch(std::integral_constant<int, -1>{});
 }
 
 }  // namespace gram
