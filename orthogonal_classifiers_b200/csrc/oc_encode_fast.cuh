@@ -502,10 +502,12 @@ __device__ __forceinline__ float* run_steps(const EncodeParams& P, int64_t img, 
 // image stride kWsStride) unless N0 == 0; ws_out: Psi_{N1} unless N1 == 10.
 constexpr int kWsStride = 1024;
 // scratch behind the two Psi buffers for the pairing sort of the half-warp chain:
-// keys (1 byte / image) | perm (int32 / slot, images + padding) | 64 ints of bins
+// keys (1 byte / image) | perm (int32: 4 image slots per warp of the packed step 4, <= chunk/2 + 32 warps)
+// | 4 x 32 ints of bins
 constexpr int kSortBins = 32;
+inline size_t encode_perm_ints(int64_t chunk) { return (size_t)(2 * chunk + 4 * kSortBins + 4); }
 inline size_t encode_sort_bytes(int64_t chunk) {
-  return (size_t)((chunk + 255) & ~(int64_t)255) + (size_t)(chunk + 2 * kSortBins) * sizeof(int32_t) +
+  return (size_t)((chunk + 255) & ~(int64_t)255) + encode_perm_ints(chunk) * sizeof(int32_t) +
          (size_t)4 * kSortBins * sizeof(int32_t) + 256;
 }
 

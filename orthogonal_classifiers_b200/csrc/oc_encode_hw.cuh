@@ -551,6 +551,300 @@ __global__ void hw_sort_scatter_kernel(const uint8_t* __restrict__ keys, int64_t
   }
 }
 
+// ---- packed step 4 ----------------------------------------------------------
+// Step 4 rotates the 2 * k non-zero rows of M_4 (k = rows the previous step kept,
+// 7..13 for MNIST-like images), i.e. k slots: with 16 lanes per image 3..9 lanes
+// idle.  The packed kernel gives an image exactly k lanes and puts floor(32 / k)
+// (<= 4) images of EQUAL k into a warp (the counting sort below makes the lists):
+// 2.5 images per warp on average instead of 2, same instruction count per warp.
+// Results do not depend on the warp's other images (hold = exact no-op).
+
+// One-sided Jacobi, odd-even ordering, on the 2 * gsz vectors of each lane group
+// [gbase, gbase + gsz), one lane per slot, NE packed pairs per vector; groups of
+// different size side by side (gsz need not be a power of two: the line does not
+// wrap, the lanes at its ends idle in round B).
+template <int NE>
+__device__ __forceinline__ int jacobi_ring(u64 (&T)[16], u64 (&S)[16], float& nT, float& nS, float thr2,
+                                           int lane, int gsz, int gbase, int mlive, int mlive_max) {
+  const int slot = lane - gbase;
+  const int src_dn = slot + 1 < gsz ? lane + 1 : gbase;
+  const int src_up = slot > 0 ? lane - 1 : gbase + gsz - 1;
+  const bool idleB = slot >= mlive - 1;
+  const unsigned gmask = (gsz >= 32 ? 0xffffffffu : ((1u << gsz) - 1u)) << gbase;
+  int sweeps = 0;
+  bool done = mlive == 0;
+#pragma unroll 1
+  for (int sw = 0; sw < kMaxSweeps; ++sw) {
+    bool again = false;
+    bool lostf = false;
+    {
+      const float fT = dot16<0, NE>(T, T), fS = dot16<0, NE>(S, S);
+      if (!done) {
+        nT = fT;
+        nS = fS;
+      }
+    }
+#pragma unroll 1
+    for (int rr = 0; rr < mlive_max; ++rr) {
+      const bool off = done || rr >= mlive;
+      rotate16<0, NE>(T, S, nT, nS, thr2, off, lostf, again);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_dn);
+      float nR = __shfl_sync(FULL, nT, src_dn);
+      rotate16<0, NE>(S, T, nS, nR, thr2, off || idleB, lostf, again);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_up);
+      nT = __shfl_sync(FULL, nR, src_up);
+      {
+        const unsigned lostmask = __ballot_sync(FULL, lostf);
+        if (lostmask) {
+          const float fT = dot16<0, NE>(T, T), fS = dot16<0, NE>(S, S);
+          if (lostmask & gmask) {
+            nT = fT;
+            nS = fS;
+          }
+          lostf = false;
+        }
+      }
+    }
+    if (!done) ++sweeps;
+    const unsigned b = __ballot_sync(FULL, again);
+    if (mlive <= 1 || !(b & gmask)) done = true;
+    if (__all_sync(FULL, done)) break;
+  }
+  return sweeps;
+}
+
+// polish16 for lane groups [gbase, gbase + gsz), one lane per slot
+template <int B2>
+__device__ __forceinline__ void polish_ring(u64 (&T)[B2], u64 (&S)[B2], float& kT, float& kS, int& rT, int& rS,
+                                            int lane, int gsz, int gbase, int mlive, int mlive_max) {
+  const int slot = lane - gbase;
+  const int src_dn = slot + 1 < gsz ? lane + 1 : gbase;
+  const int src_up = slot > 0 ? lane - 1 : gbase + gsz - 1;
+  const bool idleB = slot >= mlive - 1;
+#pragma unroll 1
+  for (int rr = 0; rr < mlive_max; ++rr) {
+    const bool off = rr >= mlive;
+    polish_pair<0, B2>(T, S, kT, kS, rT, rS, off);
+#pragma unroll
+    for (int e = 0; e < B2; ++e) T[e] = shfl2(T[e], src_dn);
+    float kR = __shfl_sync(FULL, kT, src_dn);
+    int rR = __shfl_sync(FULL, rT, src_dn);
+    polish_pair<0, B2>(S, T, kS, kR, rS, rR, off || idleB);
+#pragma unroll
+    for (int e = 0; e < B2; ++e) T[e] = shfl2(T[e], src_up);
+    kT = __shfl_sync(FULL, kR, src_up);
+    rT = __shfl_sync(FULL, rR, src_up);
+  }
+}
+
+// perm4: four image indices per warp (-1 = empty); bins[3 * kSortBins] = number of warps.
+__global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB)
+hw_row4p_kernel(const __grid_constant__ EncodeParams P, const float* __restrict__ ws_in, float* __restrict__ ws_out,
+                const int32_t* __restrict__ perm4, const int32_t* __restrict__ bins,
+                const uint8_t* __restrict__ keys) {
+  constexpr int B = 16, Q = 32, YSTR = 2 * B + 2;
+  extern __shared__ __align__(16) float smem_f[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t w = (int64_t)blockIdx.x * kHwWarps + warp;
+  if (w >= bins[3 * kSortBins]) return;  // per-warp shared memory only: no block barrier below
+  const int4 ent = __ldg(reinterpret_cast<const int4*>(perm4) + w);
+  const int k0 = ent.x >= 0 ? (int)keys[ent.x] : 0;
+  const int gs = k0 > 1 ? k0 : 1;                 // lanes (slots) per image
+  const int ipw = 32 / gs < 4 ? 32 / gs : 4;      // images of this warp
+  const int idx = lane / gs;
+  int img = idx == 0 ? ent.x : (idx == 1 ? ent.y : (idx == 2 ? ent.z : ent.w));
+  if (idx >= ipw) img = -1;
+  const bool valid = img >= 0 && img < P.N;
+  const int gsz = idx < ipw ? gs : 1;
+  const int gbase = idx < ipw ? idx * gs : lane;
+  const int slot = lane - gbase;
+  const int64_t im = valid ? img : 0;
+  const float* psi_in = ws_in + (size_t)im * kWsStride;
+  float* psi_out = ws_out + (size_t)im * kWsStride;
+  float* ysm = smem_f + (size_t)warp * 64 * YSTR;
+
+  u64 T[16], S[16];
+  {
+    const float* pt = psi_in + slot * 2 * Q;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f), s = t;
+      if (valid) {
+        t = ldg4(pt + 4 * i);
+        s = ldg4(pt + Q + 4 * i);
+      }
+      T[2 * i] = pack2(t.x, t.y); T[2 * i + 1] = pack2(t.z, t.w);
+      S[2 * i] = pack2(s.x, s.y); S[2 * i + 1] = pack2(s.z, s.w);
+    }
+  }
+  float nT = dot16<0>(T, T), nS = dot16<0>(S, S);
+  float fro = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float v = __shfl_sync(FULL, nT + nS, gbase + j);
+    if (j < gsz) fro += v;
+  }
+  const float thr2 = kFloor2 * fro;
+  const unsigned livemask = __ballot_sync(FULL, (nT + nS) > 0.f);
+  const unsigned mine = (livemask >> gbase) & ((1u << gsz) - 1u);
+  const int mlive = mine ? 32 - __clz(mine) : 0;
+  const int mlive_max = __reduce_max_sync(FULL, mlive);
+  int sweeps = 0;
+  if (mlive_max > 0) {
+    sweeps = jacobi_ring<16>(T, S, nT, nS, thr2, lane, gsz, gbase, mlive, mlive_max);
+    nT = dot16<0>(T, T);
+    nS = dot16<0>(S, S);
+  }
+  // stable descending rank among the 2 * gsz vectors of the image
+  int rT = 0, rS = 0;
+  {
+    const int pT = 2 * slot, pS = pT + 1;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float v = __shfl_sync(FULL, (j & 1) ? nS : nT, gbase + (j >> 1));
+      if (j < 2 * gsz) {
+        rT += (v > nT) || (v == nT && j < pT);
+        rS += (v > nS) || (v == nS && j < pS);
+      }
+    }
+  }
+  const Out io = make_out(P, im, 4);
+  const int r_rt = io.r_rt, b_rt = io.b_rt;
+  const bool kT = nT > thr2 && rT < r_rt;
+  const bool kS = nS > thr2 && rS < r_rt;
+  if (valid) {
+    if (io.sv) {
+      if (rT < io.sv_width) io.sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
+      if (rS < io.sv_width) io.sv[rS] = nS > thr2 ? sqrtf(nS) : 0.f;
+      for (int k = 2 * gsz + slot; k < io.sv_width; k += gsz) io.sv[k] = 0.f;
+    }
+    if (io.sweeps && slot == 0) *io.sweeps = sweeps;
+  }
+  // ---- U[(l,s), k] = (1/n_k) sum_c Psi_4[l][s*Q + c] W_k[c]  -> shared, column-major ----
+  float* yT = ysm + lane * YSTR;
+  float* yS = ysm + (32 + lane) * YSTR;
+  {
+    const float iT = kT ? 1.f / nT : 0.f;
+    const float iS = kS ? 1.f / nS : 0.f;
+#pragma unroll 1
+    for (int l = 0; l < B; ++l) {
+      float aT[2] = {0.f, 0.f}, aS[2] = {0.f, 0.f};
+      if (l < mlive_max) {  // warp-uniform; rows l >= mlive are zero
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const float* mr = psi_in + l * 2 * Q + s * Q;
+          u64 t0 = 0ull, t1 = 0ull, s0 = 0ull, s1 = 0ull;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) m = ldg4(mr + 4 * i);
+            const u64 m0 = pack2(m.x, m.y), m1 = pack2(m.z, m.w);
+            t0 = fma2(m0, T[2 * i], t0);
+            t1 = fma2(m1, T[2 * i + 1], t1);
+            s0 = fma2(m0, S[2 * i], s0);
+            s1 = fma2(m1, S[2 * i + 1], s1);
+          }
+          aT[s] = hsum2(add2(t0, t1)) * iT;
+          aS[s] = hsum2(add2(s0, s1)) * iS;
+        }
+      }
+      *reinterpret_cast<float2*>(yT + 2 * l) = make_float2(aT[0], aT[1]);
+      *reinterpret_cast<float2*>(yS + 2 * l) = make_float2(aS[0], aS[1]);
+    }
+  }
+  // ---- Psi_5: row `rank` <- vector (zero when dropped); rows >= 2 gsz are zero ----
+  if (valid) {
+    float* pT = psi_out + rT * Q;
+    float* pS = psi_out + rS * Q;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t, s;
+      unpack2(T[2 * i], t.x, t.y); unpack2(T[2 * i + 1], t.z, t.w);
+      unpack2(S[2 * i], s.x, s.y); unpack2(S[2 * i + 1], s.z, s.w);
+      if (!kT) t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!kS) s = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(pT + 4 * i) = t;
+      *reinterpret_cast<float4*>(pS + 4 * i) = s;
+    }
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 2 * gsz * (Q / 4) + slot; e < 2 * B * (Q / 4); e += gsz)
+      *reinterpret_cast<float4*>(psi_out + 4 * e) = z;
+  }
+  __syncwarp();
+  // ---- polish U (see polish_pair), normalise, A_4[(s*b + l), rank] ----
+  {
+    u64 UT[B], US[B];
+#pragma unroll
+    for (int e = 0; e < B; ++e) {
+      UT[e] = *reinterpret_cast<const u64*>(yT + 2 * e);
+      US[e] = *reinterpret_cast<const u64*>(yS + 2 * e);
+    }
+    float keyT = kT ? nT : 0.f, keyS = kS ? nS : 0.f;
+    int tagT = rT, tagS = rS;
+    polish_ring<B>(UT, US, keyT, keyS, tagT, tagS, lane, gsz, gbase, mlive, mlive_max);
+    u64 qT = 0ull, qS = 0ull;
+#pragma unroll
+    for (int e = 0; e < B; ++e) {
+      qT = fma2(UT[e], UT[e], qT);
+      qS = fma2(US[e], US[e], qS);
+    }
+    const float jT = keyT > 0.f ? rsqrtf(hsum2(qT)) : 0.f;
+    const float jS = keyS > 0.f ? rsqrtf(hsum2(qS)) : 0.f;
+    if (valid) {
+#pragma unroll
+      for (int l = 0; l < B; ++l) {
+        float t0, t1, s0, s1;
+        unpack2(UT[l], t0, t1);
+        unpack2(US[l], s0, s1);
+        if (l < b_rt) {
+          if (tagT < r_rt) {
+            io.A[l * r_rt + tagT] = t0 * jT;
+            io.A[(b_rt + l) * r_rt + tagT] = t1 * jT;
+          }
+          if (tagS < r_rt) {
+            io.A[l * r_rt + tagS] = s0 * jS;
+            io.A[(b_rt + l) * r_rt + tagS] = s1 * jS;
+          }
+        }
+      }
+      // columns >= 2 gsz of A_4 belong to vectors this image does not have: zero
+      const int c0 = 2 * gsz, nc = r_rt - c0;
+      if (nc > 0)
+        for (int e = slot; e < 2 * b_rt * nc; e += gsz) io.A[(e / nc) * r_rt + c0 + e % nc] = 0.f;
+    }
+  }
+}
+
+// counting sort for the packed kernel: bins[0..31] counts, [32..63] first warp of the bin,
+// [64..95] cursors, [96] number of warps
+__global__ void hw_pack_prefix_kernel(int32_t* __restrict__ bins) {
+  if (threadIdx.x == 0) {
+    int start = 0;
+    for (int b = kSortBins - 1; b >= 0; --b) {  // longest lines first
+      const int c = bins[b];
+      const int gs = b > 1 ? b : 1;
+      const int ipw = 32 / gs < 4 ? 32 / gs : 4;
+      bins[kSortBins + b] = start;
+      bins[2 * kSortBins + b] = 0;
+      start += (c + ipw - 1) / ipw;
+    }
+    bins[3 * kSortBins] = start;
+  }
+}
+__global__ void hw_pack_scatter_kernel(const uint8_t* __restrict__ keys, int64_t n, int32_t* __restrict__ bins,
+                                       int32_t* __restrict__ perm4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int b = keys[i] & (kSortBins - 1);
+    const int gs = b > 1 ? b : 1;
+    const int ipw = 32 / gs < 4 ? 32 / gs : 4;
+    const int pos = atomicAdd(&bins[2 * kSortBins + b], 1);
+    perm4[4 * (bins[kSortBins + b] + pos / ipw) + pos % ipw] = (int32_t)i;
+  }
+}
+
 // ---- COL steps 5, 6, 7: M_n[(s,l), c] = Psi_n[l][s*Q + c], Q = 2^(9-n) columns of
 //      length 2B = 2^(11-n).  Slot k owns columns (2k, 2k+1); one image per
 //      group of G lanes:  n  cols x len  slots  lanes/slot  G   images/warp
@@ -845,6 +1139,10 @@ inline int& sort_pairs() {
   static int v = 1;
   return v;
 }
+inline int& pack_step4() {
+  static int v = 1;
+  return v;
+}
 inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, void* sort_ws, int64_t chunk,
                                 int sms, cudaStream_t st) {
   const int per_cta = kHwWarps * 2;
@@ -854,7 +1152,7 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
   const size_t smem4 = (size_t)per_cta * ysm_floats(4) * sizeof(float);
   uint8_t* keys = reinterpret_cast<uint8_t*>(sort_ws);
   int32_t* perm = reinterpret_cast<int32_t*>(keys + ((chunk + 255) & ~(int64_t)255));
-  int32_t* bins = perm + chunk + 2 * kSortBins;
+  int32_t* bins = perm + encode_perm_ints(chunk);
   const bool sorted = sort_pairs() != 0;
   EncodeEvents& ee = encode_events();
   ee.mark(0, st);
@@ -872,7 +1170,19 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
       hw_row_kernel<3, false, false><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1, nullptr, nullptr, nullptr);
   }
   ee.mark(2, st);
-  if (sorted) {
+  if (sorted && pack_step4()) {
+    // step 4 costs (live rows) x (sweeps) per WARP: floor(32 / k) images of equal k = live rows / 2 per warp
+    const int64_t max_warps = P.N / 2 + kSortBins + 1;
+    cudaMemsetAsync(bins, 0, (size_t)4 * kSortBins * sizeof(int32_t), st);
+    cudaMemsetAsync(perm, 0xff, (size_t)4 * max_warps * sizeof(int32_t), st);
+    const int tb = 256, gb = (int)((P.N + tb - 1) / tb);
+    hw_sort_hist_kernel<<<gb, tb, 0, st>>>(keys, P.N, bins);
+    hw_pack_prefix_kernel<<<1, 32, 0, st>>>(bins);
+    hw_pack_scatter_kernel<<<gb, tb, 0, st>>>(keys, P.N, bins, perm);
+    const int grid4 = (int)((max_warps + kHwWarps - 1) / kHwWarps);
+    const size_t smem4p = (size_t)kHwWarps * 64 * 34 * sizeof(float);
+    hw_row4p_kernel<<<grid4, kHwWarps * 32, smem4p, st>>>(P, ws1, ws0, perm, bins, keys);
+  } else if (sorted) {
     // step 4 costs (live rows) x (sweeps) per WARP: pair images with equal numbers of live rows
     cudaMemsetAsync(bins, 0, (size_t)4 * kSortBins * sizeof(int32_t), st);
     const int tb = 256, gb = (int)((P.N + tb - 1) / tb);
