@@ -316,15 +316,15 @@ def main():
             "e2e_u8": {"value": world * N * args.steps / (e2e_u8_ms * 1e-3), "unit": "images/s",
                        "h2d_bytes_per_step": int(N * 784), "d2h_bytes_per_step": int(N * (16 * 4 + 4)),
                        "host_input": "uint8 pixels (MNIST's native type), pinned; /255 in the encoder load"},
-            # per step: 11 encode kernels per 131,072-image chunk (head | step 3 | 3 x pairing sort |
+            # per step: 10 encode kernels per 131,072-image chunk (Gram | steps 0-3 | 3 x counting sort |
             # step 4 | step 5 | step 6 | step 7 | steps 8-9) + overlap prep + overlap + count
-            "gpu_launches": (11 * ((N + 131071) // 131072) + 3) * args.steps,
+            "gpu_launches": (10 * ((N + 131071) // 131072) + 3) * args.steps,
             "kernels_ms": {"encode": enc_ms, "overlap": ovl_ms,
-                           "encode_launches": dict(zip(["head_0_2", "step3", "step4", "step5", "tail_6_9"],
+                           "encode_launches": dict(zip(["gram_steps_0_3", "sort", "step4", "step5", "tail_6_9"],
                                                        launch_ms))},
-            # dominant kernel: hw_row_kernel<4> (the 32 x 32 SVD step), timed with CUDA events on the
+            # dominant kernel: hw_row4p_kernel (the 32 x 32 SVD step), timed with CUDA events on the
             # launching stream inside the timed region (oc_encode_step_ms)
-            "roofline": {"bound": "fp32_fma", "kernel": "hw_row_kernel<4> (encode step 4, 32x32 SVD)",
+            "roofline": {"bound": "fp32_fma", "kernel": "hw_row4p_kernel (encode step 4, 32x32 SVD)",
                          "achieved": step4_tflops, "peak": best, "unit": "TFLOP/s",
                          "frac": step4_tflops / best if best else None,
                          "traffic": TRAFFIC_STEP4_BYTES,

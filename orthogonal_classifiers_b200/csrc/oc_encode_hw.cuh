@@ -1169,7 +1169,7 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
     else
       hw_row_kernel<3, false, false><<<grid, kHwWarps * 32, smem3, st>>>(P, ws0, ws1, nullptr, nullptr, nullptr);
   }
-  ee.mark(2, st);
+  // mark 2 (start of the step-4 kernel) is set behind the sort launches below
   if (sorted && pack_step4()) {
     // step 4 costs (live rows) x (sweeps) per WARP: floor(32 / k) images of equal k = live rows / 2 per warp
     const int64_t max_warps = P.N / 2 + kSortBins + 1;
@@ -1181,6 +1181,7 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
     hw_pack_scatter_kernel<<<gb, tb, 0, st>>>(keys, P.N, bins, perm);
     const int grid4 = (int)((max_warps + kHwWarps - 1) / kHwWarps);
     const size_t smem4p = (size_t)kHwWarps * 64 * 34 * sizeof(float);
+    ee.mark(2, st);
     hw_row4p_kernel<<<grid4, kHwWarps * 32, smem4p, st>>>(P, ws1, ws0, perm, bins, keys);
   } else if (sorted) {
     // step 4 costs (live rows) x (sweeps) per WARP: pair images with equal numbers of live rows
@@ -1190,8 +1191,10 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
     hw_sort_prefix_kernel<<<1, 32, 0, st>>>(bins, perm);
     hw_sort_scatter_kernel<<<gb, tb, 0, st>>>(keys, P.N, bins, perm);
     const int grid4 = (int)((P.N + kSortBins + per_cta - 1) / per_cta);
+    ee.mark(2, st);
     hw_row_kernel<4, true, false><<<grid4, kHwWarps * 32, smem4, st>>>(P, ws1, ws0, perm, bins + 3 * kSortBins, nullptr);
   } else {
+    ee.mark(2, st);
     hw_row_kernel<4, false, false><<<grid, kHwWarps * 32, smem4, st>>>(P, ws1, ws0, nullptr, nullptr, nullptr);
   }
   ee.mark(3, st);

@@ -167,6 +167,110 @@ __device__ __forceinline__ void mm_slices(float* __restrict__ C, int ldc, int of
   }
 }
 
+
+// ---- compile-time shapes: the natural 32 / 32 profile (L = 10, c = 5, 16 labels) ----
+// Same contractions, same operands and the same order of accumulation along k as
+// the run-time versions above, but every shape, stride and tile count is a
+// constant: each phase is one pass of <= 32 register tiles whose size is chosen
+// so that all lanes work (1024 outputs: 8 x 4, 256: 4 x 2, 64: 2 x 1, fewer: 1 x 1),
+// and the per-phase index arithmetic of mm_kmajor disappears.
+template <int W>
+__device__ __forceinline__ void ldv(float (&d)[W], const float* __restrict__ p) {
+  if constexpr (W == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+  } else if constexpr (W == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+  } else if constexpr (W == 2) {
+    const float2 a = *reinterpret_cast<const float2*>(p);
+    d[0] = a.x; d[1] = a.y;
+  } else {
+    d[0] = *p;
+  }
+}
+template <int W>
+__device__ __forceinline__ void stv(float* __restrict__ p, const float (&v)[W]) {
+  if constexpr (W == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else if constexpr (W == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  else p[0] = v[0];
+}
+
+// NS slices of C[m][n] = sum_k Xt[k][m] Y[k][n]  (M x N, k < K), slice s at C + s*OFFC, Xt + s*OFFX, Y + s*OFFY
+template <int M, int N, int K, int NS, int LDC, int OFFC, int LDX, int OFFX, int LDY, int OFFY>
+__device__ __forceinline__ void mm_static(float* __restrict__ C, const float* __restrict__ Xt,
+                                          const float* __restrict__ Y, int lane) {
+  constexpr int OUT = M * N * NS;
+  constexpr int TM = OUT >= 1024 ? 8 : (OUT >= 256 ? 4 : (OUT >= 64 ? 2 : 1));
+  constexpr int TN = OUT >= 1024 ? 4 : (OUT >= 256 ? 2 : 1);
+  static_assert(M % TM == 0 && N % TN == 0, "tile does not divide the shape");
+  constexpr int tm = M / TM, tn = N / TN, per = tm * tn, NT = per * NS;
+  static_assert(NT <= 32, "more tiles than lanes");
+  if (NT < 32 && lane >= NT) return;
+  const int s = lane / per, t = lane % per;
+  const int tj = t / tm, ti = t % tm;
+  const float* xp = Xt + s * OFFX + TM * ti;
+  const float* yp = Y + s * OFFY + TN * tj;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+#pragma unroll(K <= 8 ? K : 8)
+  for (int k = 0; k < K; ++k) {
+    float xv[TM], yv[TN];
+    ldv<TM>(xv, xp + k * LDX);
+    ldv<TN>(yv, yp + k * LDY);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+  }
+  float* cp = C + s * OFFC + (TM * ti) * LDC + TN * tj;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) stv<TN>(cp + i * LDC, acc[i]);
+}
+
+template <int NSITE>
+__device__ __forceinline__ void nat_left_step(float* E, float* Tb, const float* W, const float* A, int lane) {
+  constexpr int al = 1 << NSITE, ar = 2 << NSITE, Bl = al, Br = ar;
+  constexpr int ldE = (al + 3) & ~3, ldW = (Br + 3) & ~3, ldA = (ar + 3) & ~3, ldT = ldW;
+  // T[(s,a)][B'] = sum_B Et[B][a] W[s][B][B']
+  mm_static<al, Br, Bl, 2, ldT, al * ldT, ldE, 0, ldW, Bl * ldW>(Tb, E, W, lane);
+  __syncwarp();
+  if constexpr (NSITE + 1 < 5) {
+    // Et'[B'][a'] = sum_(s,a) T[(s,a)][B'] A[(s,a)][a']
+    mm_static<Br, ar, 2 * al, 1, ldA, 0, ldT, 0, ldA, 0>(E, Tb, A, lane);
+  } else {
+    // EL[a'][B'] = sum_(s,a) A[(s,a)][a'] T[(s,a)][B']
+    mm_static<ar, Br, 2 * al, 1, ldT, 0, ldA, 0, ldT, 0>(E, A, Tb, lane);
+  }
+  __syncwarp();
+}
+
+template <int NSITE>
+__device__ __forceinline__ void nat_right_step(float* R, float* R2, float* Tb, const float* Wt, const float* At,
+                                               int lane) {
+  constexpr int al = 1 << (10 - NSITE), ar = 1 << (9 - NSITE), Bl = al, Br = ar;
+  constexpr int ldR = (Br + 3) & ~3, ldAt = (al + 3) & ~3, ldWt = (Bl + 3) & ~3, ldTp = ldAt;
+  // T'[s][B'][a] = sum_a' R[a'][B'] At[s][a'][a]
+  mm_static<Br, al, ar, 2, ldTp, Br * ldTp, ldR, 0, ldAt, ar * ldAt>(Tb, R, At, lane);
+  __syncwarp();
+  // R'[a][B] = sum_(s,B') T'[(s,B')][a] Wt[(s,B')][B]
+  mm_static<al, Bl, 2 * Br, 1, ldWt, 0, ldTp, 0, ldWt, 0>(R2, Tb, Wt, lane);
+  __syncwarp();
+}
+
+inline bool overlap_is_natural(const OverlapParams& P) {
+  if (P.L != 10 || P.c != 5 || P.S != 16) return false;
+  for (int n = 0; n <= 10; ++n) {
+    const int b = n <= 5 ? (1 << n) : (1 << (10 - n));
+    if (P.a[n] != b || P.B[n] != b) return false;
+  }
+  return true;
+}
+
+template <bool NAT>
 __global__ void __launch_bounds__(256, 1)
 overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_constant__ OverlapFast F,
                     const float* __restrict__ small_w, const float* __restrict__ wc) {
@@ -270,6 +374,77 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
     }
     __syncwarp();
 
+    if constexpr (NAT) {
+      // ---- natural 32 / 32 profile: every shape a constant ----
+      float* E = Eb;
+      if (lane == 0) { E[0] = 1.f; Rb0[0] = 1.f; }
+      __syncwarp();
+      nat_left_step<0>(E, Tb, sW + F.w_off[0], As + F.a_off[0], lane);
+      nat_left_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], lane);
+      nat_left_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], lane);
+      nat_left_step<3>(E, Tb, sW + F.w_off[3], As + F.a_off[3], lane);
+      nat_left_step<4>(E, Tb, sW + F.w_off[4], As + F.a_off[4], lane);
+      nat_right_step<9>(Rb0, Rb1, Tb, sW + F.w_off[9], As + F.a_off[9], lane);
+      nat_right_step<8>(Rb1, Rb0, Tb, sW + F.w_off[8], As + F.a_off[8], lane);
+      nat_right_step<7>(Rb0, Rb1, Tb, sW + F.w_off[7], As + F.a_off[7], lane);
+      nat_right_step<6>(Rb1, Rb0, Tb, sW + F.w_off[6], As + F.a_off[6], lane);
+      float* R = Rb0;
+      // hairy site: al = 32, ar = 16, Bl = 32, Br = 16
+      const float* At = As + F.a_off[5];  // [s][a'][a]
+      float* G = Tb;                      // [s][a][B']
+      float* H = Tb + 1024;               // [s][B][B']
+      mm_static<32, 16, 16, 2, 16, 32 * 16, 32, 16 * 32, 16, 0>(G, At, R, lane);
+      __syncwarp();
+      mm_static<32, 16, 32, 2, 16, 32 * 16, 32, 0, 16, 32 * 16>(H, E, G, lane);
+      __syncwarp();
+      // out[l] = sum_(s,B,B') Wc[(s,B,B')][l] H[s][B][B']; lane = (label quad lq, part): rows part, part + 8, ...
+      const int lq = lane & 3, part = lane >> 2;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float4* wbase = reinterpret_cast<const float4*>(wc) + lq;
+#pragma unroll 1
+      for (int r = part; r < 64; r += 8) {
+        const float* hrow = H + r * 16;
+        const float4* wrow = wbase + (size_t)r * 16 * 4;
+        float h[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(hrow + 4 * q);
+          h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int bp = 0; bp < 16; ++bp) {
+          const float4 w = __ldg(wrow + bp * 4);
+          acc[0] = fmaf(w.x, h[bp], acc[0]);
+          acc[1] = fmaf(w.y, h[bp], acc[1]);
+          acc[2] = fmaf(w.z, h[bp], acc[2]);
+          acc[3] = fmaf(w.w, h[bp], acc[3]);
+        }
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(FULL, acc[j], o);
+      }
+      float* ov = reinterpret_cast<float*>(P.overlaps) + (size_t)img * 16;
+      float best = -1.f;
+      int besti = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = fabsf(acc[j]);
+        if (lane < 4) {
+          ov[4 * lq + j] = v;
+          if (v > best) { best = v; besti = 4 * lq + j; }
+        }
+      }
+      if (P.argmax) {
+        for (int o = 1; o < 4; o <<= 1) {
+          const float ob = __shfl_xor_sync(FULL, best, o);
+          const int oi = __shfl_xor_sync(FULL, besti, o);
+          if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) P.argmax[img] = besti;
+      }
+    } else {
     // ---- left sweep.  State Et[B][a] (ld r4(a)); the last step leaves EL[a][B] ----
     float* E = Eb;
     if (lane == 0) E[0] = 1.f;
@@ -370,8 +545,14 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
         if (lane == 0) P.argmax[img] = besti;
       }
     }
+    }  // !NAT
     __syncwarp();
   }
+}
+
+inline int& overlap_static_shapes() {
+  static int v = 1;
+  return v;
 }
 
 // Host-side plan; returns false when the shapes do not fit the fast kernel.
@@ -434,13 +615,18 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   const size_t smem = wbytes + tabbytes + (size_t)warps * PER_WARP * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    e = cudaFuncSetAttribute(overlap_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    e = cudaFuncSetAttribute(overlap_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(overlap_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t need = (P.N + warps - 1) / warps;
   const int grid = (int)(need < sms ? need : sms);
-  overlap_fast_kernel<<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+  if (overlap_static_shapes() && overlap_is_natural(P) && F.Spad == 16)
+    overlap_fast_kernel<true><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+  else
+    overlap_fast_kernel<false><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
