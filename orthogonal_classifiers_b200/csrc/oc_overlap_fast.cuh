@@ -359,7 +359,11 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
 #pragma unroll
       for (int j = 0; j < kOvPre; ++j) {
         const int v = lane + 32 * j;
-        if (4 * v < stride) {
+        if (NAT && v >= 1 && v <= 340) {
+          // sites 1..4 of the natural profile keep their layout ([s][a][a'], no row padding):
+          // a straight 128-bit copy, 4 floats further on (site 0 is padded from 4 to 8 floats)
+          *reinterpret_cast<float4*>(As + 4 * v + 4) = pre[j];
+        } else if (4 * v < stride) {
           const uint2 t = *reinterpret_cast<const uint2*>(tab + 4 * v);
           As[t.x & 0xffff] = pre[j].x;
           As[t.x >> 16] = pre[j].y;
@@ -397,27 +401,27 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       __syncwarp();
       mm_static<32, 16, 32, 2, 16, 32 * 16, 32, 0, 16, 32 * 16>(H, E, G, lane);
       __syncwarp();
-      // out[l] = sum_(s,B,B') Wc[(s,B,B')][l] H[s][B][B']; lane = (label quad lq, part): rows part, part + 8, ...
-      const int lq = lane & 3, part = lane >> 2;
+      // out[l] = sum_(s,B,B') Wc[(s,B,B')][l] H[s][B][B'].  Wc is [(s,B)][B'][l] = 64 rows of 1 KB:
+      // lane = (B' mod 8, label quad), so one warp load is 512 contiguous bytes (half a row);
+      // 32 loads in flight per lane hide the L2 latency (Wc, 64 KB, does not fit the L1 left
+      // beside 213 KB of shared memory).  Issuing the first loads ahead of the H contraction
+      // was tried and did not pay (the next image's 22 prefetch registers are live as well).
+      const int lq = lane & 3, bpl = lane >> 2;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const float4* wbase = reinterpret_cast<const float4*>(wc) + lq;
+      const float4* wl = reinterpret_cast<const float4*>(wc) + lane;  // (bp = bpl, lq): float4 index bp * 4 + lq
+      const float* hl = H + bpl;
 #pragma unroll 1
-      for (int r = part; r < 64; r += 8) {
-        const float* hrow = H + r * 16;
-        const float4* wrow = wbase + (size_t)r * 16 * 4;
-        float h[16];
+      for (int r0 = 0; r0 < 64; r0 += 16) {
+        float4 wv[32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(hrow + 4 * q);
-          h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
-        }
+        for (int j = 0; j < 32; ++j) wv[j] = __ldg(wl + (size_t)(r0 + (j >> 1)) * 64 + (j & 1) * 32);
 #pragma unroll
-        for (int bp = 0; bp < 16; ++bp) {
-          const float4 w = __ldg(wrow + bp * 4);
-          acc[0] = fmaf(w.x, h[bp], acc[0]);
-          acc[1] = fmaf(w.y, h[bp], acc[1]);
-          acc[2] = fmaf(w.z, h[bp], acc[2]);
-          acc[3] = fmaf(w.w, h[bp], acc[3]);
+        for (int j = 0; j < 32; ++j) {
+          const float h = hl[(r0 + (j >> 1)) * 16 + (j & 1) * 8];
+          acc[0] = fmaf(wv[j].x, h, acc[0]);
+          acc[1] = fmaf(wv[j].y, h, acc[1]);
+          acc[2] = fmaf(wv[j].z, h, acc[2]);
+          acc[3] = fmaf(wv[j].w, h, acc[3]);
         }
       }
 #pragma unroll
