@@ -30,10 +30,10 @@ FLOP_ENCODE = 1_210_241      # SURVEY.md §8(d), algorithmic, per image
 FLOP_STEP4 = 721_920         # the 32 x 32 SVD step (bond 4 -> 5), the dominant kernel
 FLOP_CLASSIFY = 257_456
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
-# (hw_row_kernel<4>, 70,000 images) from `ncu --set full` of this command
-# (profiles/ncu_step4_r1.csv: 293.03 MB read + 519.70 MB written; algorithmic
-# 3 x 4 KB per image = 860 MB)
-TRAFFIC_STEP4_BYTES = 812_730_880
+# (hw_row4p_kernel, 70,000 images) from `ncu --set full` of this command
+# (profiles/ncu_step4_r1.csv: 198.00 MB read + 521.01 MB written; algorithmic
+# <= 3 x 4 KB per image = 860 MB: Psi_4 live rows in, Psi_5 and A_4 out)
+TRAFFIC_STEP4_BYTES = 719_006_720
 BYTES_IMG = 784 * 4 + 16 * 4 + 4
 
 

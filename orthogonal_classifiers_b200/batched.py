@@ -38,6 +38,13 @@ def set_force_generic(flag: bool) -> None:
     check(lib.oc_set_option(b"force_generic", int(bool(flag))))
 
 
+def set_option(key: str, value: int) -> None:
+    """``oc_set_option`` (include/oc_b200.h): implementation switches used by the
+    tests and the timing scripts — ``enc_gram`` (Gram front end of the encoder),
+    ``enc_pack`` (packed step 4), ``ov_static`` (compile-time overlap shapes), ..."""
+    check(lib.oc_set_option(key.encode(), int(value)))
+
+
 def n_sites_for(n_pix: int) -> int:
     """tools.py:218 — L = ceil(log2(n_pix))."""
     return max(1, int(np.ceil(np.log2(n_pix))))

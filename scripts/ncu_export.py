@@ -1,0 +1,19 @@
+"""Key metrics of the first kernel in an .ncu-rep as `metric,unit,value` lines:
+python scripts/ncu_export.py report.ncu-rep > profiles/xxx.csv"""
+import csv, io, subprocess, sys
+out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units, vals = rows[0], rows[1], rows[2]
+want = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed']
+w = csv.writer(sys.stdout)
+w.writerow(['metric', 'unit', 'value'])
+for j, h in enumerate(hdr):
+    if h in want or (h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio')):
+        w.writerow([h, units[j], vals[j]])

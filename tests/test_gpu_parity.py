@@ -225,6 +225,52 @@ def test_generic_and_specialised_kernels_agree(gpu_lib):
             assert np.abs(ov_fast - ov_gen).max() <= 1e-5 * ov_gen.max()
 
 
+@pytest.mark.parametrize("option", ["enc_gram", "enc_pack", "ov_static"])
+def test_alternative_code_paths_agree(gpu_lib, option):
+    """Every fast path has its predecessor behind an option: the Gram-matrix front
+    end (steps 0-3) vs. the Jacobi head kernels, the packed step 4 vs. the paired
+    one, the compile-time overlap shapes vs. the run-time ones.  Same
+    gauge-invariants from both."""
+    from orthogonal_classifiers_b200 import batched
+    imgs = np.concatenate([synthetic_images(300, seed=21), adversarial_images()]).astype(np.float32)
+    clf = random_classifier(10, 32, centre=5, seed=4)
+    for D in (32, 20):
+        new = gpu_lib.encode_images(imgs, D, return_svals=True)
+        ov_new = gpu_lib.label_overlaps(new, clf) if D == 32 else None
+        batched.set_option(option, 0)
+        try:
+            old = gpu_lib.encode_images(imgs, D, return_svals=True)
+            ov_old = gpu_lib.label_overlaps(old, clf) if D == 32 else None
+        finally:
+            batched.set_option(option, 1)
+        sn, so = new.svals.cpu().numpy(), old.svals.cpu().numpy()
+        assert np.abs(sn - so).max() <= 1e-5 * so.max()
+        for i in (0, 7, 150, 299, len(imgs) - 1):
+            a = oracle.mps_to_state([x.astype(np.float64) for x in new.sites_numpy(i)])
+            b = oracle.mps_to_state([x.astype(np.float64) for x in old.sites_numpy(i)])
+            assert _state_err(a, b) < 1e-5
+        if D == 32:
+            assert np.abs(ov_new - ov_old).max() <= 1e-5 * ov_old.max()
+
+
+def test_encoding_does_not_depend_on_batch_composition(gpu_lib):
+    """Images share warps (two per warp in most kernels, up to four of equal
+    live-row count in the packed step 4, chosen by a device-side counting sort
+    with atomics): an image's MPS must be bit-identical whatever else is in the
+    batch and in whatever order."""
+    imgs = synthetic_images(257, seed=23).astype(np.float32)
+    full = gpu_lib.encode_images(imgs, 32)
+    perm = np.random.default_rng(0).permutation(len(imgs))
+    shuffled = gpu_lib.encode_images(imgs[perm], 32)
+    alone = gpu_lib.encode_images(imgs[5:6], 32)
+    for i in (0, 5, 100, 256):
+        j = int(np.where(perm == i)[0][0])
+        for x, y in zip(full.sites_numpy(i), shuffled.sites_numpy(j)):
+            np.testing.assert_array_equal(x, y)
+    for x, y in zip(full.sites_numpy(5), alone.sites_numpy(0)):
+        np.testing.assert_array_equal(x, y)
+
+
 def test_host_pipeline_matches_single_shot(gpu_lib):
     """Chunked, copy/compute-overlapped host API == one-shot classify, bit-exact."""
     import torch
