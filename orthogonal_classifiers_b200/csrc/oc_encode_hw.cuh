@@ -51,8 +51,8 @@ __device__ __forceinline__ float4 ld4(const float* p) {
 
 // dot product of two 32-element register vectors, summed over the LP lanes of a slot
 // (NE < 16: only the first NE packed pairs can be non-zero)
-template <int LOGLP, int NE = 16>
-__device__ __forceinline__ float dot16(const u64 (&a)[16], const u64 (&b)[16]) {
+template <int LOGLP, int NE = 16, int NA>
+__device__ __forceinline__ float dot16(const u64 (&a)[NA], const u64 (&b)[NA]) {
   u64 acc[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) acc[e] = mul2(a[e], b[e]);
@@ -71,8 +71,8 @@ __device__ __forceinline__ float dot16(const u64 (&a)[16], const u64 (&b)[16]) {
 // ends in round B, and everything a finished / shorter half-warp still has to
 // sit through while its partner image works, so that the result for an image
 // never depends on which image shares its warp.
-template <int LOGLP, int NE = 16>
-__device__ __forceinline__ void rotate16(u64 (&a)[16], u64 (&b)[16], float& na, float& nb, float thr2,
+template <int LOGLP, int NE = 16, int NA>
+__device__ __forceinline__ void rotate16(u64 (&a)[NA], u64 (&b)[NA], float& na, float& nb, float thr2,
                                          bool hold, bool& lostf, bool& again) {
   const float ab = dot16<LOGLP, NE>(a, b);
   const float aa = na, bb = nb;
@@ -563,8 +563,8 @@ __global__ void hw_sort_scatter_kernel(const uint8_t* __restrict__ keys, int64_t
 // [gbase, gbase + gsz), one lane per slot, NE packed pairs per vector; groups of
 // different size side by side (gsz need not be a power of two: the line does not
 // wrap, the lanes at its ends idle in round B).
-template <int NE>
-__device__ __forceinline__ int jacobi_ring(u64 (&T)[16], u64 (&S)[16], float& nT, float& nS, float thr2,
+template <int NE, int NA>
+__device__ __forceinline__ int jacobi_ring(u64 (&T)[NA], u64 (&S)[NA], float& nT, float& nS, float thr2,
                                            int lane, int gsz, int gbase, int mlive, int mlive_max) {
   const int slot = lane - gbase;
   const int src_dn = slot + 1 < gsz ? lane + 1 : gbase;
@@ -814,6 +814,236 @@ hw_row4p_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
       if (nc > 0)
         for (int e = slot; e < 2 * b_rt * nc; e += gsz) io.A[(e / nc) * r_rt + c0 + e % nc] = 0.f;
     }
+  }
+}
+
+// ---- packed step 4, QR-preconditioned ----------------------------------------
+// M_4 (2k rows of 32) = L Q with Q's rows orthonormal: the left singular vectors
+// of M_4 are those of the SMALL factor L (2k x 2k), so the Jacobi iteration runs
+// on the columns of L - vectors of 2k <= 26 elements instead of 32, 5.1 sweeps
+// instead of 7.1 (rows of R = L^T are closer to orthogonal than the rows of M_4:
+// Drmac-Veselic preconditioning, here without pivoting, the rows arrive sorted
+// by the previous step's singular values) - and U comes out of the iteration
+// directly (normalised columns): no back-substitution, no Gram-Schmidt polish.
+// L by one pass of modified Gram-Schmidt on the rows in registers (R is backward
+// stable even where Q is not orthonormal; Q is not used).  Psi_5 = U^T M_4.
+// Needs k <= 13 (n_pix <= 832).  Same warp lists as hw_row4p_kernel.
+constexpr int kQ4NE = 13;   // packed pairs of an L column: 2k <= 26 elements
+constexpr int kQ4RS = 28;   // floats per row of R in shared memory
+__global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB)
+hw_row4q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict__ ws_in, float* __restrict__ ws_out,
+                const int32_t* __restrict__ perm4, const int32_t* __restrict__ bins,
+                const uint8_t* __restrict__ keys) {
+  constexpr int B = 16, Q = 32;
+  extern __shared__ __align__(16) float smem_f[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t w = (int64_t)blockIdx.x * kHwWarps + warp;
+  if (w >= bins[3 * kSortBins]) return;  // per-warp shared memory only: no block barrier below
+  const int4 ent = __ldg(reinterpret_cast<const int4*>(perm4) + w);
+  const int k0 = ent.x >= 0 ? (int)keys[ent.x] : 0;
+  const int gs = k0 > 1 ? k0 : 1;
+  const int ipw = 32 / gs < 4 ? 32 / gs : 4;
+  const int idx = lane / gs;
+  int img = idx == 0 ? ent.x : (idx == 1 ? ent.y : (idx == 2 ? ent.z : ent.w));
+  if (idx >= ipw) img = -1;
+  const bool valid = img >= 0 && img < P.N;
+  const bool ingrp = idx < ipw;
+  const int gsz = ingrp ? gs : 1;
+  const int gbase = ingrp ? idx * gs : lane;
+  const int slot = lane - gbase;
+  const int64_t im = valid ? img : 0;
+  const float* psi_in = ws_in + (size_t)im * kWsStride;
+  float* psi_out = ws_out + (size_t)im * kWsStride;
+  float* Rw = smem_f + (size_t)warp * 64 * kQ4RS;  // R[j][i] of the image at row 2 * gbase + j
+
+  float thr2;
+  {
+    // ---- rows (2 slot, 2 slot + 1) of M_4 -> registers; MGS, natural order ----
+    u64 T[16], S[16];
+    {
+      const float* pt = psi_in + slot * 2 * Q;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f), s = t;
+        if (valid) {
+          t = ldg4(pt + 4 * i);
+          s = ldg4(pt + Q + 4 * i);
+        }
+        T[2 * i] = pack2(t.x, t.y); T[2 * i + 1] = pack2(t.z, t.w);
+        S[2 * i] = pack2(s.x, s.y); S[2 * i + 1] = pack2(s.z, s.w);
+      }
+    }
+    const float n0 = dot16<0>(T, T) + dot16<0>(S, S);
+    float fro = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float v = __shfl_sync(FULL, n0, gbase + j);
+      if (j < gsz) fro += v;
+    }
+    thr2 = kFloor2 * fro;
+    const int vT = 2 * slot, vS = vT + 1;
+    float* rrow = Rw + (size_t)(2 * gbase) * kQ4RS + vT;
+#pragma unroll 1
+    for (int jj = 0; jj < gs; ++jj) {
+      const int owner = gbase + (jj < gsz ? jj : 0);
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        const int j = 2 * jj + par;
+        u64 qv[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) qv[e] = shfl2(par ? S[e] : T[e], owner);
+        const float qn2 = dot16<0>(qv, qv);
+        const bool livej = qn2 > thr2;
+        const float inv2 = livej ? 1.f / qn2 : 0.f, invn = livej ? rsqrtf(qn2) : 0.f;
+        float rT = dot16<0>(qv, T), rS = dot16<0>(qv, S);
+        if (vT <= j) rT = 0.f;
+        if (vS <= j) rS = 0.f;
+        const float cT = -rT * inv2, cS = -rS * inv2;
+        const u64 cT2 = pack2(cT, cT), cS2 = pack2(cS, cS);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          T[e] = fma2(cT2, qv[e], T[e]);
+          S[e] = fma2(cS2, qv[e], S[e]);
+        }
+        if (ingrp && jj < gsz) {
+          const float dg = qn2 * invn;  // |q_j|: the diagonal of R
+          *reinterpret_cast<float2*>(rrow + (size_t)j * kQ4RS) =
+              make_float2(vT == j ? dg : rT * invn, vS == j ? dg : rS * invn);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // ---- columns (2 slot, 2 slot + 1) of L = rows of R -> registers ----
+  u64 T[kQ4NE], S[kQ4NE];
+  {
+    const float* r0 = Rw + (size_t)(2 * gbase + 2 * slot) * kQ4RS;
+#pragma unroll
+    for (int e = 0; e < kQ4NE; ++e) {
+      float2 a = make_float2(0.f, 0.f), b = a;
+      if (ingrp && e < gsz) {
+        a = *reinterpret_cast<const float2*>(r0 + 2 * e);
+        b = *reinterpret_cast<const float2*>(r0 + kQ4RS + 2 * e);
+      }
+      T[e] = pack2(a.x, a.y);
+      S[e] = pack2(b.x, b.y);
+    }
+  }
+  float nT = dot16<0, kQ4NE>(T, T), nS = dot16<0, kQ4NE>(S, S);
+  const unsigned livemask = __ballot_sync(FULL, (nT + nS) > 0.f);
+  const unsigned mine = (livemask >> gbase) & ((1u << gsz) - 1u);
+  const int mlive = mine ? 32 - __clz(mine) : 0;
+  const int mlive_max = __reduce_max_sync(FULL, mlive);
+  int sweeps = 0;
+  if (mlive_max > 0) {
+    sweeps = jacobi_ring<kQ4NE>(T, S, nT, nS, thr2, lane, gsz, gbase, mlive, mlive_max);
+    nT = dot16<0, kQ4NE>(T, T);
+    nS = dot16<0, kQ4NE>(S, S);
+  }
+  int rT = 0, rS = 0;
+  {
+    const int pT = 2 * slot, pS = pT + 1;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float v = __shfl_sync(FULL, (j & 1) ? nS : nT, gbase + (j >> 1));
+      if (j < 2 * gsz) {
+        rT += (v > nT) || (v == nT && j < pT);
+        rS += (v > nS) || (v == nS && j < pS);
+      }
+    }
+  }
+  const Out io = make_out(P, im, 4);
+  const int r_rt = io.r_rt, b_rt = io.b_rt;
+  const bool kT = nT > thr2 && rT < r_rt;
+  const bool kS = nS > thr2 && rS < r_rt;
+  if (valid) {
+    if (io.sv) {
+      if (rT < io.sv_width) io.sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
+      if (rS < io.sv_width) io.sv[rS] = nS > thr2 ? sqrtf(nS) : 0.f;
+      for (int k = 2 * gsz + slot; k < io.sv_width; k += gsz) io.sv[k] = 0.f;
+    }
+    if (io.sweeps && slot == 0) *io.sweeps = sweeps;
+  }
+  // ---- U = normalised columns: U[2l + s][vector];  A_4[(s*b + l), rank] ----
+  {
+    const float iT = kT ? rsqrtf(nT) : 0.f, iS = kS ? rsqrtf(nS) : 0.f;
+    const u64 iT2 = pack2(iT, iT), iS2 = pack2(iS, iS);
+#pragma unroll
+    for (int e = 0; e < kQ4NE; ++e) {
+      T[e] = mul2(T[e], iT2);
+      S[e] = mul2(S[e], iS2);
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int l = 0; l < B; ++l) {
+      float t0 = 0.f, t1 = 0.f, s0 = 0.f, s1 = 0.f;
+      if (l < kQ4NE) {
+        unpack2(T[l < kQ4NE ? l : 0], t0, t1);
+        unpack2(S[l < kQ4NE ? l : 0], s0, s1);
+      }
+      if (l < b_rt) {
+        if (rT < r_rt) {
+          io.A[l * r_rt + rT] = t0;
+          io.A[(b_rt + l) * r_rt + rT] = t1;
+        }
+        if (rS < r_rt) {
+          io.A[l * r_rt + rS] = s0;
+          io.A[(b_rt + l) * r_rt + rS] = s1;
+        }
+      }
+    }
+    const int c0 = 2 * gsz, nc = r_rt - c0;
+    if (nc > 0)
+      for (int e = slot; e < 2 * b_rt * nc; e += gsz) io.A[(e / nc) * r_rt + c0 + e % nc] = 0.f;
+  }
+  // ---- Psi_5[rank][c] = sum_i U[i][vector] M_4[i][c], two passes of 16 columns ----
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    u64 aT[8], aS[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) aT[q] = aS[q] = 0ull;
+#pragma unroll
+    for (int e = 0; e < kQ4NE; ++e) {
+      if (e < gs) {  // warp-uniform; rows i >= 2 gs of M_4 (and of U) are zero
+        float t0, t1, s0, s1;
+        unpack2(T[e], t0, t1);
+        unpack2(S[e], s0, s1);
+#pragma unroll
+        for (int sdx = 0; sdx < 2; ++sdx) {
+          const u64 ut = sdx ? pack2(t1, t1) : pack2(t0, t0);
+          const u64 us = sdx ? pack2(s1, s1) : pack2(s0, s0);
+          const float* mr = psi_in + e * 2 * Q + sdx * Q + 16 * half;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) m = ldg4(mr + 4 * q4);
+            const u64 m0 = pack2(m.x, m.y), m1 = pack2(m.z, m.w);
+            aT[2 * q4] = fma2(ut, m0, aT[2 * q4]);
+            aT[2 * q4 + 1] = fma2(ut, m1, aT[2 * q4 + 1]);
+            aS[2 * q4] = fma2(us, m0, aS[2 * q4]);
+            aS[2 * q4 + 1] = fma2(us, m1, aS[2 * q4 + 1]);
+          }
+        }
+      }
+    }
+    if (valid) {
+      float* pT = psi_out + rT * Q + 16 * half;
+      float* pS = psi_out + rS * Q + 16 * half;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        float4 t, s;
+        unpack2(aT[2 * q4], t.x, t.y); unpack2(aT[2 * q4 + 1], t.z, t.w);
+        unpack2(aS[2 * q4], s.x, s.y); unpack2(aS[2 * q4 + 1], s.z, s.w);
+        *reinterpret_cast<float4*>(pT + 4 * q4) = t;
+        *reinterpret_cast<float4*>(pS + 4 * q4) = s;
+      }
+    }
+  }
+  if (valid) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 2 * gsz * (Q / 4) + slot; e < 2 * B * (Q / 4); e += gsz)
+      *reinterpret_cast<float4*>(psi_out + 4 * e) = z;
   }
 }
 
@@ -1143,6 +1373,10 @@ inline int& pack_step4() {
   static int v = 1;
   return v;
 }
+inline int& mgs_step4() {
+  static int v = 1;
+  return v;
+}
 inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, void* sort_ws, int64_t chunk,
                                 int sms, cudaStream_t st) {
   const int per_cta = kHwWarps * 2;
@@ -1182,7 +1416,11 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
     const int grid4 = (int)((max_warps + kHwWarps - 1) / kHwWarps);
     const size_t smem4p = (size_t)kHwWarps * 64 * 34 * sizeof(float);
     ee.mark(2, st);
-    hw_row4p_kernel<<<grid4, kHwWarps * 32, smem4p, st>>>(P, ws1, ws0, perm, bins, keys);
+    if (mgs_step4() && P.n_pix <= 64 * kQ4NE)
+      hw_row4q_kernel<<<grid4, kHwWarps * 32, (size_t)kHwWarps * 64 * kQ4RS * sizeof(float), st>>>(P, ws1, ws0, perm,
+                                                                                                bins, keys);
+    else
+      hw_row4p_kernel<<<grid4, kHwWarps * 32, smem4p, st>>>(P, ws1, ws0, perm, bins, keys);
   } else if (sorted) {
     // step 4 costs (live rows) x (sweeps) per WARP: pair images with equal numbers of live rows
     cudaMemsetAsync(bins, 0, (size_t)4 * kSortBins * sizeof(int32_t), st);
