@@ -830,6 +830,145 @@ hw_row4p_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
 // Needs k <= 13 (n_pix <= 832).  Same warp lists as hw_row4p_kernel.
 constexpr int kQ4NE = 13;   // packed pairs of an L column: 2k <= 26 elements
 constexpr int kQ4RS = 28;   // floats per row of R in shared memory
+// Everything behind the factorisation, for L columns of NE packed pairs (2 gs <= 2 NE elements)
+template <int NE>
+__device__ __forceinline__ void q4_tail(const EncodeParams& P, bool valid, bool ingrp, int gs, int gsz, int gbase,
+                                        int slot, int lane, int64_t im, const float* __restrict__ psi_in,
+                                        float* __restrict__ psi_out, const float* __restrict__ Rw, float thr2) {
+  constexpr int B = 16, Q = 32;
+  // ---- columns (2 slot, 2 slot + 1) of L = rows of R -> registers ----
+  u64 T[NE], S[NE];
+  {
+    const float* r0 = Rw + (size_t)(2 * gbase + 2 * slot) * kQ4RS;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      float2 a = make_float2(0.f, 0.f), b = a;
+      if (ingrp && e < gsz) {
+        a = *reinterpret_cast<const float2*>(r0 + 2 * e);
+        b = *reinterpret_cast<const float2*>(r0 + kQ4RS + 2 * e);
+      }
+      T[e] = pack2(a.x, a.y);
+      S[e] = pack2(b.x, b.y);
+    }
+  }
+  float nT = dot16<0, NE>(T, T), nS = dot16<0, NE>(S, S);
+  const unsigned livemask = __ballot_sync(FULL, (nT + nS) > 0.f);
+  const unsigned mine = (livemask >> gbase) & ((1u << gsz) - 1u);
+  const int mlive = mine ? 32 - __clz(mine) : 0;
+  const int mlive_max = __reduce_max_sync(FULL, mlive);
+  int sweeps = 0;
+  if (mlive_max > 0) {
+    sweeps = jacobi_ring<NE>(T, S, nT, nS, thr2, lane, gsz, gbase, mlive, mlive_max);
+    nT = dot16<0, NE>(T, T);
+    nS = dot16<0, NE>(S, S);
+  }
+  int rT = 0, rS = 0;
+  {
+    const int pT = 2 * slot, pS = pT + 1;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float v = __shfl_sync(FULL, (j & 1) ? nS : nT, gbase + (j >> 1));
+      if (j < 2 * gsz) {
+        rT += (v > nT) || (v == nT && j < pT);
+        rS += (v > nS) || (v == nS && j < pS);
+      }
+    }
+  }
+  const Out io = make_out(P, im, 4);
+  const int r_rt = io.r_rt, b_rt = io.b_rt;
+  const bool kT = nT > thr2 && rT < r_rt;
+  const bool kS = nS > thr2 && rS < r_rt;
+  if (valid) {
+    if (io.sv) {
+      if (rT < io.sv_width) io.sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
+      if (rS < io.sv_width) io.sv[rS] = nS > thr2 ? sqrtf(nS) : 0.f;
+      for (int k = 2 * gsz + slot; k < io.sv_width; k += gsz) io.sv[k] = 0.f;
+    }
+    if (io.sweeps && slot == 0) *io.sweeps = sweeps;
+  }
+  // ---- U = normalised columns: U[2l + s][vector];  A_4[(s*b + l), rank] ----
+  {
+    const float iT = kT ? rsqrtf(nT) : 0.f, iS = kS ? rsqrtf(nS) : 0.f;
+    const u64 iT2 = pack2(iT, iT), iS2 = pack2(iS, iS);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      T[e] = mul2(T[e], iT2);
+      S[e] = mul2(S[e], iS2);
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int l = 0; l < B; ++l) {
+      float t0 = 0.f, t1 = 0.f, s0 = 0.f, s1 = 0.f;
+      if (l < NE) {
+        unpack2(T[l < NE ? l : 0], t0, t1);
+        unpack2(S[l < NE ? l : 0], s0, s1);
+      }
+      if (l < b_rt) {
+        if (rT < r_rt) {
+          io.A[l * r_rt + rT] = t0;
+          io.A[(b_rt + l) * r_rt + rT] = t1;
+        }
+        if (rS < r_rt) {
+          io.A[l * r_rt + rS] = s0;
+          io.A[(b_rt + l) * r_rt + rS] = s1;
+        }
+      }
+    }
+    const int c0 = 2 * gsz, nc = r_rt - c0;
+    if (nc > 0)
+      for (int e = slot; e < 2 * b_rt * nc; e += gsz) io.A[(e / nc) * r_rt + c0 + e % nc] = 0.f;
+  }
+  // ---- Psi_5[rank][c] = sum_i U[i][vector] M_4[i][c], two passes of 16 columns ----
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    u64 aT[8], aS[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) aT[q] = aS[q] = 0ull;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      if (e < gs) {  // warp-uniform; rows i >= 2 gs of M_4 (and of U) are zero
+        float t0, t1, s0, s1;
+        unpack2(T[e], t0, t1);
+        unpack2(S[e], s0, s1);
+#pragma unroll
+        for (int sdx = 0; sdx < 2; ++sdx) {
+          const u64 ut = sdx ? pack2(t1, t1) : pack2(t0, t0);
+          const u64 us = sdx ? pack2(s1, s1) : pack2(s0, s0);
+          const float* mr = psi_in + e * 2 * Q + sdx * Q + 16 * half;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) m = ldg4(mr + 4 * q4);
+            const u64 m0 = pack2(m.x, m.y), m1 = pack2(m.z, m.w);
+            aT[2 * q4] = fma2(ut, m0, aT[2 * q4]);
+            aT[2 * q4 + 1] = fma2(ut, m1, aT[2 * q4 + 1]);
+            aS[2 * q4] = fma2(us, m0, aS[2 * q4]);
+            aS[2 * q4 + 1] = fma2(us, m1, aS[2 * q4 + 1]);
+          }
+        }
+      }
+    }
+    if (valid) {
+      float* pT = psi_out + rT * Q + 16 * half;
+      float* pS = psi_out + rS * Q + 16 * half;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        float4 t, s;
+        unpack2(aT[2 * q4], t.x, t.y); unpack2(aT[2 * q4 + 1], t.z, t.w);
+        unpack2(aS[2 * q4], s.x, s.y); unpack2(aS[2 * q4 + 1], s.z, s.w);
+        *reinterpret_cast<float4*>(pT + 4 * q4) = t;
+        *reinterpret_cast<float4*>(pS + 4 * q4) = s;
+      }
+    }
+  }
+  if (valid) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 2 * gsz * (Q / 4) + slot; e < 2 * B * (Q / 4); e += gsz)
+      *reinterpret_cast<float4*>(psi_out + 4 * e) = z;
+  }
+}
+
 __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB)
 hw_row4q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict__ ws_in, float* __restrict__ ws_out,
                 const int32_t* __restrict__ perm4, const int32_t* __restrict__ bins,
@@ -914,137 +1053,10 @@ hw_row4q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
     }
   }
   __syncwarp();
-  // ---- columns (2 slot, 2 slot + 1) of L = rows of R -> registers ----
-  u64 T[kQ4NE], S[kQ4NE];
-  {
-    const float* r0 = Rw + (size_t)(2 * gbase + 2 * slot) * kQ4RS;
-#pragma unroll
-    for (int e = 0; e < kQ4NE; ++e) {
-      float2 a = make_float2(0.f, 0.f), b = a;
-      if (ingrp && e < gsz) {
-        a = *reinterpret_cast<const float2*>(r0 + 2 * e);
-        b = *reinterpret_cast<const float2*>(r0 + kQ4RS + 2 * e);
-      }
-      T[e] = pack2(a.x, a.y);
-      S[e] = pack2(b.x, b.y);
-    }
-  }
-  float nT = dot16<0, kQ4NE>(T, T), nS = dot16<0, kQ4NE>(S, S);
-  const unsigned livemask = __ballot_sync(FULL, (nT + nS) > 0.f);
-  const unsigned mine = (livemask >> gbase) & ((1u << gsz) - 1u);
-  const int mlive = mine ? 32 - __clz(mine) : 0;
-  const int mlive_max = __reduce_max_sync(FULL, mlive);
-  int sweeps = 0;
-  if (mlive_max > 0) {
-    sweeps = jacobi_ring<kQ4NE>(T, S, nT, nS, thr2, lane, gsz, gbase, mlive, mlive_max);
-    nT = dot16<0, kQ4NE>(T, T);
-    nS = dot16<0, kQ4NE>(S, S);
-  }
-  int rT = 0, rS = 0;
-  {
-    const int pT = 2 * slot, pS = pT + 1;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-      const float v = __shfl_sync(FULL, (j & 1) ? nS : nT, gbase + (j >> 1));
-      if (j < 2 * gsz) {
-        rT += (v > nT) || (v == nT && j < pT);
-        rS += (v > nS) || (v == nS && j < pS);
-      }
-    }
-  }
-  const Out io = make_out(P, im, 4);
-  const int r_rt = io.r_rt, b_rt = io.b_rt;
-  const bool kT = nT > thr2 && rT < r_rt;
-  const bool kS = nS > thr2 && rS < r_rt;
-  if (valid) {
-    if (io.sv) {
-      if (rT < io.sv_width) io.sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
-      if (rS < io.sv_width) io.sv[rS] = nS > thr2 ? sqrtf(nS) : 0.f;
-      for (int k = 2 * gsz + slot; k < io.sv_width; k += gsz) io.sv[k] = 0.f;
-    }
-    if (io.sweeps && slot == 0) *io.sweeps = sweeps;
-  }
-  // ---- U = normalised columns: U[2l + s][vector];  A_4[(s*b + l), rank] ----
-  {
-    const float iT = kT ? rsqrtf(nT) : 0.f, iS = kS ? rsqrtf(nS) : 0.f;
-    const u64 iT2 = pack2(iT, iT), iS2 = pack2(iS, iS);
-#pragma unroll
-    for (int e = 0; e < kQ4NE; ++e) {
-      T[e] = mul2(T[e], iT2);
-      S[e] = mul2(S[e], iS2);
-    }
-  }
-  if (valid) {
-#pragma unroll
-    for (int l = 0; l < B; ++l) {
-      float t0 = 0.f, t1 = 0.f, s0 = 0.f, s1 = 0.f;
-      if (l < kQ4NE) {
-        unpack2(T[l < kQ4NE ? l : 0], t0, t1);
-        unpack2(S[l < kQ4NE ? l : 0], s0, s1);
-      }
-      if (l < b_rt) {
-        if (rT < r_rt) {
-          io.A[l * r_rt + rT] = t0;
-          io.A[(b_rt + l) * r_rt + rT] = t1;
-        }
-        if (rS < r_rt) {
-          io.A[l * r_rt + rS] = s0;
-          io.A[(b_rt + l) * r_rt + rS] = s1;
-        }
-      }
-    }
-    const int c0 = 2 * gsz, nc = r_rt - c0;
-    if (nc > 0)
-      for (int e = slot; e < 2 * b_rt * nc; e += gsz) io.A[(e / nc) * r_rt + c0 + e % nc] = 0.f;
-  }
-  // ---- Psi_5[rank][c] = sum_i U[i][vector] M_4[i][c], two passes of 16 columns ----
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    u64 aT[8], aS[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) aT[q] = aS[q] = 0ull;
-#pragma unroll
-    for (int e = 0; e < kQ4NE; ++e) {
-      if (e < gs) {  // warp-uniform; rows i >= 2 gs of M_4 (and of U) are zero
-        float t0, t1, s0, s1;
-        unpack2(T[e], t0, t1);
-        unpack2(S[e], s0, s1);
-#pragma unroll
-        for (int sdx = 0; sdx < 2; ++sdx) {
-          const u64 ut = sdx ? pack2(t1, t1) : pack2(t0, t0);
-          const u64 us = sdx ? pack2(s1, s1) : pack2(s0, s0);
-          const float* mr = psi_in + e * 2 * Q + sdx * Q + 16 * half;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) m = ldg4(mr + 4 * q4);
-            const u64 m0 = pack2(m.x, m.y), m1 = pack2(m.z, m.w);
-            aT[2 * q4] = fma2(ut, m0, aT[2 * q4]);
-            aT[2 * q4 + 1] = fma2(ut, m1, aT[2 * q4 + 1]);
-            aS[2 * q4] = fma2(us, m0, aS[2 * q4]);
-            aS[2 * q4 + 1] = fma2(us, m1, aS[2 * q4 + 1]);
-          }
-        }
-      }
-    }
-    if (valid) {
-      float* pT = psi_out + rT * Q + 16 * half;
-      float* pS = psi_out + rS * Q + 16 * half;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        float4 t, s;
-        unpack2(aT[2 * q4], t.x, t.y); unpack2(aT[2 * q4 + 1], t.z, t.w);
-        unpack2(aS[2 * q4], s.x, s.y); unpack2(aS[2 * q4 + 1], s.z, s.w);
-        *reinterpret_cast<float4*>(pT + 4 * q4) = t;
-        *reinterpret_cast<float4*>(pS + 4 * q4) = s;
-      }
-    }
-  }
-  if (valid) {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e = 2 * gsz * (Q / 4) + slot; e < 2 * B * (Q / 4); e += gsz)
-      *reinterpret_cast<float4*>(psi_out + 4 * e) = z;
-  }
+  // vectors of 2 gs elements: the rotation cost is proportional to the padded length
+  if (gs <= 8) q4_tail<8>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
+  else if (gs <= 10) q4_tail<10>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
+  else q4_tail<kQ4NE>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
 }
 
 // counting sort for the packed kernel: bins[0..31] counts, [32..63] first warp of the bin,
