@@ -51,8 +51,8 @@ __device__ __forceinline__ float4 ld4(const float* p) {
 
 // dot product of two 32-element register vectors, summed over the LP lanes of a slot
 // (NE < 16: only the first NE packed pairs can be non-zero)
-template <int LOGLP, int NE = 16, int NA>
-__device__ __forceinline__ float dot16(const u64 (&a)[NA], const u64 (&b)[NA]) {
+template <int LOGLP, int NE = 16, int NA, int NB>
+__device__ __forceinline__ float dot16(const u64 (&a)[NA], const u64 (&b)[NB]) {
   u64 acc[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) acc[e] = mul2(a[e], b[e]);
@@ -177,7 +177,7 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
 // singular value (key) is orthogonalised against the other; nothing else
 // changes, so the well-determined columns keep their accuracy.  Keys and rank
 // tags travel with the columns (positions swap as in the Jacobi ordering).
-template <int LOGLP, int B2>
+template <int LOGLP, int B2, bool SPREAD = false>
 __device__ __forceinline__ void polish_pair(u64 (&a)[B2], u64 (&b)[B2], float& ka, float& kb, int& ra, int& rb,
                                             bool hold) {
   u64 acc0 = mul2(a[0], b[0]), acc1 = 0ull;
@@ -187,7 +187,11 @@ __device__ __forceinline__ void polish_pair(u64 (&a)[B2], u64 (&b)[B2], float& k
     if (e & 1) acc1 = fma2(a[e], b[e], acc1);
     else acc0 = fma2(a[e], b[e], acc0);
   }
-  const float g = hsum2(add2(acc0, acc1));
+  float g = hsum2(add2(acc0, acc1));
+  if constexpr (SPREAD) {  // the columns are spread over the LP lanes of the slot
+#pragma unroll
+    for (int o = 0; o < LOGLP; ++o) g += __shfl_xor_sync(FULL, g, 1 << o);
+  }
   // a' = s x + c y,  b' = c x + ns y  (swap);  hold: identity
   const bool a_big = ka >= kb;
   const float c = hold ? 0.f : 1.f;
@@ -210,7 +214,7 @@ __device__ __forceinline__ void polish_pair(u64 (&a)[B2], u64 (&b)[B2], float& k
   }
 }
 
-template <int LOGLP, int B2>
+template <int LOGLP, int B2, bool SPREAD = false>
 __device__ __forceinline__ void polish16(u64 (&T)[B2], u64 (&S)[B2], float& kT, float& kS, int& rT, int& rS,
                                          int lane, int mlive, int mlive_max) {
   constexpr int LP = 1 << LOGLP;
@@ -223,13 +227,13 @@ __device__ __forceinline__ void polish16(u64 (&T)[B2], u64 (&S)[B2], float& kT, 
 #pragma unroll 1
   for (int rr = 0; rr < mlive_max; ++rr) {
     const bool off = rr >= mlive;
-    polish_pair<LOGLP, B2>(T, S, kT, kS, rT, rS, off);
+    polish_pair<LOGLP, B2, SPREAD>(T, S, kT, kS, rT, rS, off);
     if (M > 1) {
 #pragma unroll
       for (int e = 0; e < B2; ++e) T[e] = shfl2(T[e], src_dn);
       float kR = __shfl_sync(FULL, kT, src_dn);
       int rR = __shfl_sync(FULL, rT, src_dn);
-      polish_pair<LOGLP, B2>(S, T, kS, kR, rS, rR, off || idleB);
+      polish_pair<LOGLP, B2, SPREAD>(S, T, kS, kR, rS, rR, off || idleB);
 #pragma unroll
       for (int e = 0; e < B2; ++e) T[e] = shfl2(T[e], src_up);
       kT = __shfl_sync(FULL, kR, src_up);
@@ -1263,6 +1267,234 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col_kernel(const
   }
 }
 
+// ---- step 5, QR-preconditioned ---------------------------------------------------
+// M_5 (64 x 16, columns spread over the two lanes of a slot) = Q R by one pass of
+// column-pivoted modified Gram-Schmidt in registers; the right singular vectors and
+// the singular values come from one-sided Jacobi on the rows of the SMALL factor R
+// (16 vectors of 16 elements, 5.1 sweeps; the 64-element columns took 7.0), whose
+// converged vectors sigma_r v_r ARE the rows of Psi_6.  U = M_5 V Sigma^-1 is one
+// product; its columns lose orthogonality like sigma_max / sigma_r, which one sweep
+// of Gram-Schmidt projections (smaller sigma against larger, as in the row steps)
+// restores (numpy model: 6e-4 -> 2e-7).  NE = packed pairs per lane and column:
+// 13 when rows l >= 26 of Psi_5 are structurally zero (n_pix <= 832), else 16.
+template <int NE>
+__global__ void __launch_bounds__(kHwWarps * 32, 3)
+hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict__ ws_in, float* __restrict__ ws_out) {
+  constexpr int Q = 16;
+  __shared__ __align__(16) float Rsm[kHwWarps * 2 * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lg = lane & 15, hb = lane & 16, h = lane >> 4;
+  const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
+  const bool valid = img < P.N;
+  const int64_t im = valid ? img : 0;
+  const float* psi = ws_in + (size_t)im * kWsStride;  // [32][2Q]
+  const int slot = lg >> 1, sub = lg & 1;
+  float* R = Rsm + (size_t)(warp * 2 + h) * 256;  // R[step][column]
+  // lane's elements: (s = sub, l = 0 .. 2 NE - 1); packed pair j = (l = 2j, 2j + 1)
+  u64 T[16], S[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) T[j] = S[j] = 0ull;
+  {
+    const float* pc = psi + sub * Q + 2 * slot;
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      float2 v0 = make_float2(0.f, 0.f), v1 = v0;
+      if (valid) {
+        v0 = __ldg(reinterpret_cast<const float2*>(pc + (2 * j) * 2 * Q));
+        v1 = __ldg(reinterpret_cast<const float2*>(pc + (2 * j + 1) * 2 * Q));
+      }
+      T[j] = pack2(v0.x, v1.x);
+      S[j] = pack2(v0.y, v1.y);
+    }
+  }
+  float nT = dot16<1, NE>(T, T), nS = dot16<1, NE>(S, S);
+  const float fro = group_sum<4>(sub == 0 ? nT + nS : 0.f);
+  const float thr2 = kFloor2 * fro;
+  // ---- column-pivoted MGS; R[step][c] -> shared ----
+  int nsteps = 0;  // R rows up to the last live pivot
+  {
+#pragma unroll 1
+    for (int step = 0; step < Q; ++step) {
+      // pivot: largest remaining (cached, downdated) squared norm; ties -> lowest column
+      unsigned key = 0u;
+      {
+        const unsigned kt = nT > 0.f ? ((__float_as_uint(nT) & ~15u) | (unsigned)(15 - 2 * slot)) : 0u;
+        const unsigned ks = nS > 0.f ? ((__float_as_uint(nS) & ~15u) | (unsigned)(14 - 2 * slot)) : 0u;
+        key = kt > ks ? kt : ks;
+#pragma unroll
+        for (int o = 2; o < 16; o <<= 1) {
+          const unsigned other = __shfl_xor_sync(FULL, key, o);
+          key = key > other ? key : other;
+        }
+      }
+      const int pc = 15 - (int)(key & 15u);
+      const int owner = hb | (((pc >> 1) << 1) | sub);
+      u64 qv[NE];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) qv[e] = shfl2((pc & 1) ? S[e] : T[e], owner);
+      const float qn2 = dot16<1, NE>(qv, qv);
+      // the cached norms only ORDER the pivots; a column whose true residual is below the floor is
+      // retired as dead (zero row of R) and the factorisation goes on with the others
+      const bool dead = key == 0u || !(qn2 > thr2);
+      const float inv2 = dead ? 0.f : 1.f / qn2, invn = dead ? 0.f : rsqrtf(qn2);
+      float rT = dot16<1, NE>(qv, T), rS = dot16<1, NE>(qv, S);
+      const bool isT = 2 * slot == pc, isS = 2 * slot + 1 == pc;
+      if (!(nT > 0.f) || isT) rT = 0.f;  // finished columns (norm < 0) and the pivot itself stay
+      if (!(nS > 0.f) || isS) rS = 0.f;
+      const float cT = -rT * inv2, cS = -rS * inv2;
+      const u64 cT2 = pack2(cT, cT), cS2 = pack2(cS, cS);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        T[e] = fma2(cT2, qv[e], T[e]);
+        S[e] = fma2(cS2, qv[e], S[e]);
+      }
+      if (sub == 0) {
+        const float dg = qn2 * invn;
+        *reinterpret_cast<float2*>(R + step * Q + 2 * slot) =
+            make_float2(isT ? dg : rT * invn, isS ? dg : rS * invn);
+      }
+      // downdate the cached norms; the pivot column is finished
+      nT = isT ? -1.f : (nT > 0.f ? fmaxf(fmaf(cT, rT, nT), 1e-37f) : nT);
+      nS = isS ? -1.f : (nS > 0.f ? fmaxf(fmaf(cS, rS, nS), 1e-37f) : nS);
+      if (!dead) nsteps = step + 1;
+    }
+  }
+  __syncwarp();
+  // ---- Jacobi on the rows of R (vector j = R[j][.], 8 elements per lane) ----
+#pragma unroll
+  for (int j = 0; j < 16; ++j) T[j] = S[j] = 0ull;
+  {
+    const float* r0 = R + (2 * slot) * Q + 8 * sub;
+    const float4 a0 = lds4(r0), a1 = lds4(r0 + 4), b0 = lds4(r0 + Q), b1 = lds4(r0 + Q + 4);
+    T[0] = pack2(a0.x, a0.y); T[1] = pack2(a0.z, a0.w); T[2] = pack2(a1.x, a1.y); T[3] = pack2(a1.z, a1.w);
+    S[0] = pack2(b0.x, b0.y); S[1] = pack2(b0.z, b0.w); S[2] = pack2(b1.x, b1.y); S[3] = pack2(b1.z, b1.w);
+  }
+  nT = dot16<1, 4>(T, T);
+  nS = dot16<1, 4>(S, S);
+  const int mlive = (nsteps + 1) >> 1;
+  int mlive_max = mlive;
+  mlive_max = max(mlive_max, __shfl_xor_sync(FULL, mlive_max, 16));
+  int sweeps = 0;
+  if (mlive_max > 0) {
+    sweeps = jacobi16<1, 4, 4>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+    nT = dot16<1, 4>(T, T);
+    nS = dot16<1, 4>(S, S);
+  }
+  int rT, rS;
+  rank16<1, 4>(nT, nS, lane, rT, rS);
+  const Out io = make_out(P, im, 5);
+  const int r_rt = io.r_rt, b_rt = io.b_rt;
+  const bool kT = nT > thr2 && rT < r_rt;
+  const bool kS = nS > thr2 && rS < r_rt;
+  if (valid) {
+    if (io.sv) {
+      if (sub == 0) {
+        if (rT < io.sv_width) io.sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
+        if (rS < io.sv_width) io.sv[rS] = nS > thr2 ? sqrtf(nS) : 0.f;
+      }
+      for (int k = Q + lg; k < io.sv_width; k += 16) io.sv[k] = 0.f;
+    }
+    if (io.sweeps && lg == 0) *io.sweeps = sweeps;
+    // Psi_6[rank][c] = sigma_r v_r[c]: the converged vector itself
+    float* out = ws_out + (size_t)im * kWsStride + 8 * sub;
+    float4 t0, t1, s0, s1;
+    unpack2(T[0], t0.x, t0.y); unpack2(T[1], t0.z, t0.w); unpack2(T[2], t1.x, t1.y); unpack2(T[3], t1.z, t1.w);
+    unpack2(S[0], s0.x, s0.y); unpack2(S[1], s0.z, s0.w); unpack2(S[2], s1.x, s1.y); unpack2(S[3], s1.z, s1.w);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rT < Q) {
+      *reinterpret_cast<float4*>(out + rT * Q) = kT ? t0 : z;
+      *reinterpret_cast<float4*>(out + rT * Q + 4) = kT ? t1 : z;
+    }
+    if (rS < Q) {
+      *reinterpret_cast<float4*>(out + rS * Q) = kS ? s0 : z;
+      *reinterpret_cast<float4*>(out + rS * Q + 4) = kS ? s1 : z;
+    }
+  }
+  // ---- U = M_5 V Sigma^-1: coefficients (sigma v)[c] / sigma^2 of both columns, all 16 c ----
+  u64 cf[16];  // cf[c] = (coefficient of column T, of column S)
+  {
+    const float iT = kT ? 1.f / nT : 0.f, iS = kS ? 1.f / nS : 0.f;
+    float vt[8], vs[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      unpack2(T[e], vt[2 * e], vt[2 * e + 1]);
+      unpack2(S[e], vs[2 * e], vs[2 * e + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float mt = vt[i] * iT, ms = vs[i] * iS;
+      const float ot = __shfl_xor_sync(FULL, mt, 1), os = __shfl_xor_sync(FULL, ms, 1);
+      // this lane holds c = 8 sub + i, its partner c = 8 (1 - sub) + i
+      cf[i] = sub ? pack2(ot, os) : pack2(mt, ms);
+      cf[8 + i] = sub ? pack2(mt, ms) : pack2(ot, os);
+    }
+  }
+  u64 UT[NE], US[NE];
+  {
+    const float* pr = psi + sub * Q;
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      u64 acc[2] = {0ull, 0ull};  // (U_T, U_S) of elements l = 2j, 2j + 1
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const float* row = pr + (2 * j + p) * 2 * Q;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) m = ldg4(row + 4 * q4);
+          acc[p] = fma2(cf[4 * q4], pack2(m.x, m.x), acc[p]);
+          acc[p] = fma2(cf[4 * q4 + 1], pack2(m.y, m.y), acc[p]);
+          acc[p] = fma2(cf[4 * q4 + 2], pack2(m.z, m.z), acc[p]);
+          acc[p] = fma2(cf[4 * q4 + 3], pack2(m.w, m.w), acc[p]);
+        }
+      }
+      float a0, b0, a1, b1;
+      unpack2(acc[0], a0, b0);
+      unpack2(acc[1], a1, b1);
+      UT[j] = pack2(a0, a1);
+      US[j] = pack2(b0, b1);
+    }
+  }
+  // ---- polish (one odd-even sweep of projections), normalise, A_5[(s*b + l), rank] ----
+  {
+    float keyT = kT ? nT : 0.f, keyS = kS ? nS : 0.f;
+    int tagT = rT, tagS = rS;
+    polish16<1, NE, true>(UT, US, keyT, keyS, tagT, tagS, lane, mlive, mlive_max);
+    u64 qT = 0ull, qS = 0ull;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      qT = fma2(UT[e], UT[e], qT);
+      qS = fma2(US[e], US[e], qS);
+    }
+    float sT = hsum2(qT), sS = hsum2(qS);
+    sT += __shfl_xor_sync(FULL, sT, 1);
+    sS += __shfl_xor_sync(FULL, sS, 1);
+    const float jT = keyT > 0.f ? rsqrtf(sT) : 0.f;
+    const float jS = keyS > 0.f ? rsqrtf(sS) : 0.f;
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        float t0, t1, s0, s1;
+        unpack2(UT[j], t0, t1);
+        unpack2(US[j], s0, s1);
+        const int la = 2 * j, lb = la + 1;
+        if (la < b_rt) {
+          if (tagT < r_rt) io.A[(sub * b_rt + la) * r_rt + tagT] = t0 * jT;
+          if (tagS < r_rt) io.A[(sub * b_rt + la) * r_rt + tagS] = s0 * jS;
+        }
+        if (lb < b_rt) {
+          if (tagT < r_rt) io.A[(sub * b_rt + lb) * r_rt + tagT] = t1 * jT;
+          if (tagS < r_rt) io.A[(sub * b_rt + lb) * r_rt + tagS] = s1 * jS;
+        }
+      }
+      // rows l >= 2 NE are structurally zero
+      const int nz = (b_rt - 2 * NE) * r_rt;
+      if (nz > 0)
+        for (int e = lg; e < 2 * nz; e += 16) io.A[((e / nz) * b_rt + 2 * NE) * r_rt + e % nz] = 0.f;
+    }
+  }
+}
+
 // ---- steps 8 and 9, one THREAD per image: Psi_8 is 4 x 4 ----
 __global__ void __launch_bounds__(128) hw_tail89_kernel(const __grid_constant__ EncodeParams P,
                                                         const float* __restrict__ ws_in) {
@@ -1389,6 +1621,10 @@ inline int& mgs_step4() {
   static int v = 1;
   return v;
 }
+inline int& qr_step5() {
+  static int v = 1;
+  return v;
+}
 inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, void* sort_ws, int64_t chunk,
                                 int sms, cudaStream_t st) {
   const int per_cta = kHwWarps * 2;
@@ -1448,7 +1684,12 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
     hw_row_kernel<4, false, false><<<grid, kHwWarps * 32, smem4, st>>>(P, ws1, ws0, nullptr, nullptr, nullptr);
   }
   ee.mark(3, st);
-  hw_col_kernel<5><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
+  if (qr_step5() && P.n_pix <= 832)
+    hw_col5q_kernel<13><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
+  else if (qr_step5())
+    hw_col5q_kernel<16><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
+  else
+    hw_col_kernel<5><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
   ee.mark(4, st);
   // tail: steps 6 and 7 with 8 / 16 images per warp, steps 8-9 one thread per image
   const int ipc6 = kHwWarps * ColShape<6>::IPW, ipc7 = kHwWarps * ColShape<7>::IPW;
