@@ -30,10 +30,10 @@ FLOP_ENCODE = 1_210_241      # SURVEY.md §8(d), algorithmic, per image
 FLOP_STEP4 = 721_920         # the 32 x 32 SVD step (bond 4 -> 5), the dominant kernel
 FLOP_CLASSIFY = 257_456
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
-# (hw_row4p_kernel, 70,000 images) from `ncu --set full` of this command
-# (profiles/ncu_step4_r1.csv: 198.00 MB read + 521.01 MB written; algorithmic
+# (hw_row4q_kernel, 70,000 images) from `ncu --set full` of this command
+# (profiles/ncu_step4_r1.csv: 206.38 MB read + 523.97 MB written; algorithmic
 # <= 3 x 4 KB per image = 860 MB: Psi_4 live rows in, Psi_5 and A_4 out)
-TRAFFIC_STEP4_BYTES = 719_006_720
+TRAFFIC_STEP4_BYTES = 730_351_360
 BYTES_IMG = 784 * 4 + 16 * 4 + 4
 
 
@@ -322,9 +322,9 @@ def main():
             "kernels_ms": {"encode": enc_ms, "overlap": ovl_ms,
                            "encode_launches": dict(zip(["gram_steps_0_3", "sort", "step4", "step5", "tail_6_9"],
                                                        launch_ms))},
-            # dominant kernel: hw_row4p_kernel (the 32 x 32 SVD step), timed with CUDA events on the
+            # dominant kernel: hw_row4q_kernel (the 32 x 32 SVD step), timed with CUDA events on the
             # launching stream inside the timed region (oc_encode_step_ms)
-            "roofline": {"bound": "fp32_fma", "kernel": "hw_row4p_kernel (encode step 4, 32x32 SVD)",
+            "roofline": {"bound": "fp32_fma", "kernel": "hw_row4q_kernel (encode step 4, 32x32 SVD)",
                          "achieved": step4_tflops, "peak": best, "unit": "TFLOP/s",
                          "frac": step4_tflops / best if best else None,
                          "traffic": TRAFFIC_STEP4_BYTES,
@@ -333,7 +333,7 @@ def main():
                          "peak_source": "fp32 FMA microbenchmark (oc_fma_peak_launch) in this run; "
                                         "MEASURED_PEAKS.json has no fp32 figure (hbm_gbs / bf16 only); nominal 74.4",
                          "why_not_hbm_or_tensor": "458 FLOP/B (HBM bound would be 2.0 G img/s) and no GEMM-shaped "
-                                                  "work: one-sided Jacobi on 32-vectors (DESIGN.md §4)",
+                                                  "work: Gram-Schmidt + one-sided Jacobi on vectors of 16-32 (DESIGN.md §4)",
                          "encode": {"achieved": enc_tflops, "frac": enc_tflops / best if best else None,
                                     "algorithmic_flop_per_image": FLOP_ENCODE},
                          "path_frac": (FLOP_ENCODE + FLOP_CLASSIFY) * N * args.steps / (ms * 1e-3) / 1e12 / best
