@@ -1278,7 +1278,7 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col_kernel(const
 // restores (numpy model: 6e-4 -> 2e-7).  NE = packed pairs per lane and column:
 // 13 when rows l >= 26 of Psi_5 are structurally zero (n_pix <= 832), else 16.
 template <int NE>
-__global__ void __launch_bounds__(kHwWarps * 32, 3)
+__global__ void __launch_bounds__(kHwWarps * 32, 4)
 hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict__ ws_in, float* __restrict__ ws_out) {
   constexpr int Q = 16;
   __shared__ __align__(16) float Rsm[kHwWarps * 2 * 256];
