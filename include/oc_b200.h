@@ -53,8 +53,18 @@ extern "C" {
 int oc_version(void);
 const char* oc_last_error(void);
 
-/* Test/diagnostic switches.  "force_generic" = 1 routes every call through the
- * runtime-shaped kernels instead of the specialised ones (both are CUDA). */
+/* Test/diagnostic switches (every alternative is CUDA; there is no CPU path).
+ *   "force_generic" = 1  every call through the runtime-shaped kernels
+ *   "enc_hw"   = 0  D > 16 encodes with the one-image-per-warp kernels
+ *   "enc_gram" = 0  steps 0-3 by Jacobi on the image unfoldings instead of the
+ *                   16 x 16 Gram matrix
+ *   "enc_pack" = 0  step 4 with 16 lanes per image instead of packed warps
+ *   "enc_mgs4" = 0  step 4 without the Gram-Schmidt preconditioning
+ *   "enc_qr5"  = 0  step 5 without the pivoted Gram-Schmidt preconditioning
+ *   "enc_sort" = 0  no device-side sort of the images by live rows
+ *   "ov_static" = 0 run-time shapes in the overlap kernel for the 32/32 profile
+ *   "enc_events"    see oc_encode_step_ms
+ * Unknown keys return OC_E_ARG. */
 int oc_set_option(const char* key, int value);
 
 /* Shape helper for the fixed-shape MPS batch.
@@ -147,8 +157,8 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N,
 
 /* Diagnostics: per-launch device times of the encoder.  After
  * oc_set_option("enc_events", 1) every oc_encode_batch records a CUDA event on
- * its stream before and after each kernel of the step-major chain (head |
- * step 3 | step 4 | step 5 | tail; first chunk of the call only), keeping the
+ * its stream around the five parts of the step-major chain (Gram + steps 0-3 |
+ * sort | step 4 | step 5 | steps 6-9; first chunk of the call only), keeping the
  * last 16 calls.  oc_encode_step_ms synchronises on those events and returns
  * the elapsed milliseconds of the `n` launches (n <= 5) averaged over the
  * recorded calls; used by bench.py for the roofline of the dominant kernel
