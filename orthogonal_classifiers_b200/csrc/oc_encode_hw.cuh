@@ -528,8 +528,15 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_row_kernel(const
 // ---- pairing sort: images with the same number of live rows share a warp ----
 // bins[0..31] counts, bins[32..63] starts (even-padded), bins[64..95] cursors, bins[96] = total slots
 __global__ void hw_sort_hist_kernel(const uint8_t* __restrict__ keys, int64_t n, int32_t* __restrict__ bins) {
+  // block-local histogram in shared memory, one global atomic per non-empty bin and block
+  // (the keys take ~7 values: 70,000 global atomics on 7 addresses serialise)
+  __shared__ int sh[kSortBins];
+  if (threadIdx.x < kSortBins) sh[threadIdx.x] = 0;
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicAdd(&bins[keys[i] & (kSortBins - 1)], 1);
+  if (i < n) atomicAdd(&sh[keys[i] & (kSortBins - 1)], 1);
+  __syncthreads();
+  if (threadIdx.x < kSortBins && sh[threadIdx.x]) atomicAdd(&bins[threadIdx.x], sh[threadIdx.x]);
 }
 __global__ void hw_sort_prefix_kernel(int32_t* __restrict__ bins, int32_t* __restrict__ perm) {
   if (threadIdx.x == 0) {
@@ -1081,12 +1088,25 @@ __global__ void hw_pack_prefix_kernel(int32_t* __restrict__ bins) {
 }
 __global__ void hw_pack_scatter_kernel(const uint8_t* __restrict__ keys, int64_t n, int32_t* __restrict__ bins,
                                        int32_t* __restrict__ perm4) {
+  // positions inside a bin: block-local ranks from shared-memory atomics + one global atomic per
+  // non-empty bin and block for the block's base
+  __shared__ int sh[kSortBins], base[kSortBins];
+  if (threadIdx.x < kSortBins) sh[threadIdx.x] = 0;
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int b = 0, local = 0;
   if (i < n) {
-    const int b = keys[i] & (kSortBins - 1);
+    b = keys[i] & (kSortBins - 1);
+    local = atomicAdd(&sh[b], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < kSortBins && sh[threadIdx.x])
+    base[threadIdx.x] = atomicAdd(&bins[2 * kSortBins + threadIdx.x], sh[threadIdx.x]);
+  __syncthreads();
+  if (i < n) {
     const int gs = b > 1 ? b : 1;
     const int ipw = 32 / gs < 4 ? 32 / gs : 4;
-    const int pos = atomicAdd(&bins[2 * kSortBins + b], 1);
+    const int pos = base[b] + local;
     perm4[4 * (bins[kSortBins + b] + pos / ipw) + pos % ipw] = (int32_t)i;
   }
 }
