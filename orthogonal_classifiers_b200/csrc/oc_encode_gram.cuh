@@ -174,39 +174,53 @@ __global__ void __launch_bounds__(kHwWarps * 32, 3) gram_kernel(const __grid_con
         acc2[a][b] = fma(av[a], cv[b], acc2[a][b]);
       }
   }
-  // sum over the four k-quarters (lanes l16 ^ 4, l16 ^ 8)
+  // sum over the four k-quarters (lanes l16 ^ 4, l16 ^ 8).  Diagonal block: all-reduce of its
+  // 10 entries, stored by the kq = 0 lanes.  Off-diagonal blocks: reduce-scatter - after the
+  // two exchanges the lane holds ONE fully summed row (a = 2 (kq & 1) + (kq >> 1)) of each
+  // block, so every lane stores 2 x 4 entries and their mirrors, no divergence.
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      if (b <= a) {
-        acc0[a][b] += shfl_xor_d(acc0[a][b], 4);
-        acc0[a][b] += shfl_xor_d(acc0[a][b], 8);
-      }
-      acc1[a][b] += shfl_xor_d(acc1[a][b], 4);
-      acc1[a][b] += shfl_xor_d(acc1[a][b], 8);
-      acc2[a][b] += shfl_xor_d(acc2[a][b], 4);
-      acc2[a][b] += shfl_xor_d(acc2[a][b], 8);
+    for (int b = 0; b <= a; ++b) {
+      acc0[a][b] += shfl_xor_d(acc0[a][b], 4);
+      acc0[a][b] += shfl_xor_d(acc0[a][b], 8);
     }
-  if (valid) {
-    double* g = g_out + (size_t)img * kGStride;
-    // kq = 0 writes the diagonal block, 1 the (ia, ia+1) block and its mirror, 2 the (ia, ia+2) one
+  const bool b2 = kq & 1, b3 = kq >> 1;
+  double f1[4], f2[4];
+  {
+    double r1[2][4], r2[2][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int ap = 0; ap < 2; ++ap)
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        const int ra = 4 * ia + a;
-        if (kq == 0 && b <= a) {
-          g[ra * 16 + 4 * ia + b] = acc0[a][b];
-          g[(4 * ia + b) * 16 + ra] = acc0[a][b];
-        } else if (kq == 1) {
-          g[ra * 16 + 4 * ib1 + b] = acc1[a][b];
-          g[(4 * ib1 + b) * 16 + ra] = acc1[a][b];
-        } else if (kq == 2) {
-          g[ra * 16 + 4 * ib2 + b] = acc2[a][b];
-          g[(4 * ib2 + b) * 16 + ra] = acc2[a][b];
-        }
+        r1[ap][b] = (b2 ? acc1[ap + 2][b] : acc1[ap][b]) + shfl_xor_d(b2 ? acc1[ap][b] : acc1[ap + 2][b], 4);
+        r2[ap][b] = (b2 ? acc2[ap + 2][b] : acc2[ap][b]) + shfl_xor_d(b2 ? acc2[ap][b] : acc2[ap + 2][b], 4);
       }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      f1[b] = (b3 ? r1[1][b] : r1[0][b]) + shfl_xor_d(b3 ? r1[0][b] : r1[1][b], 8);
+      f2[b] = (b3 ? r2[1][b] : r2[0][b]) + shfl_xor_d(b3 ? r2[0][b] : r2[1][b], 8);
+    }
+  }
+  if (valid) {
+    double* g = g_out + (size_t)img * kGStride;
+    if (kq == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          g[(4 * ia + a) * 16 + 4 * ia + b] = acc0[a][b];
+          g[(4 * ia + b) * 16 + 4 * ia + a] = acc0[a][b];
+        }
+    }
+    const int ra = 4 * ia + 2 * (kq & 1) + (kq >> 1);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      g[ra * 16 + 4 * ib1 + b] = f1[b];
+      g[(4 * ib1 + b) * 16 + ra] = f1[b];
+      g[ra * 16 + 4 * ib2 + b] = f2[b];
+      g[(4 * ib2 + b) * 16 + ra] = f2[b];
+    }
   }
 }
 
