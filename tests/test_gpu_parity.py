@@ -271,6 +271,26 @@ def test_encoding_does_not_depend_on_batch_composition(gpu_lib):
         np.testing.assert_array_equal(x, y)
 
 
+def test_chunk_boundary_of_the_encoder(gpu_lib):
+    """The encoder works in chunks of 131,072 images (workspace and sort lists are
+    per chunk): images on both sides of the boundary must come out as they do in
+    a small batch."""
+    import torch
+    base = synthetic_images(512, seed=29).astype(np.float32)
+    n = 131072 + 700
+    reps = (n + len(base) - 1) // len(base)
+    big = torch.from_numpy(np.tile(base, (reps, 1))[:n]).cuda()
+    clf = gpu_lib.DeviceClassifier(random_classifier(10, 32, centre=5, seed=6))
+    from orthogonal_classifiers_b200 import batched
+    ov_big, am_big = batched.classify_device(big, clf, 32)
+    ov_small, am_small = batched.classify_device(big[:512].contiguous(), clf, 32)
+    ov_big, am_big = ov_big.cpu().numpy(), am_big.cpu().numpy()
+    ov_small, am_small = ov_small.cpu().numpy(), am_small.cpu().numpy()
+    for i in (0, 131071, 131072, 131073, n - 1):
+        np.testing.assert_array_equal(ov_big[i], ov_small[i % 512])
+        assert am_big[i] == am_small[i % 512]
+
+
 def test_host_pipeline_matches_single_shot(gpu_lib):
     """Chunked, copy/compute-overlapped host API == one-shot classify, bit-exact."""
     import torch
