@@ -197,7 +197,18 @@ __device__ __forceinline__ void stv(float* __restrict__ p, const float (&v)[W]) 
 }
 
 // NS slices of C[m][n] = sum_k Xt[k][m] Y[k][n]  (M x N, k < K), slice s at C + s*OFFC, Xt + s*OFFX, Y + s*OFFY
-template <int M, int N, int K, int NS, int LDC, int OFFC, int LDX, int OFFX, int LDY, int OFFY>
+// Bank swizzles of the buffers the tensor-core contractions read as fragments (lane = (g, t)
+// loads element (k0 + t, c0 + g)): with rows of 32 floats the four k rows of a fragment would
+// sit on the same banks, so column c of row k is stored at c ^ ((k & 3) << 3); with rows of 16,
+// at c ^ (((k >> 1) & 1) << 3).  Multiples of 8: float2 / float4 accesses stay contiguous.
+template <int SW>
+__device__ __forceinline__ int swz(int k, int col) {
+  if constexpr (SW == 32) return col ^ ((k & 3) << 3);
+  else if constexpr (SW == 16) return col ^ (((k >> 1) & 1) << 3);
+  else return col;
+}
+
+template <int M, int N, int K, int NS, int LDC, int OFFC, int LDX, int OFFX, int LDY, int OFFY, int CSW = 0>
 __device__ __forceinline__ void mm_static(float* __restrict__ C, const float* __restrict__ Xt,
                                           const float* __restrict__ Y, int lane) {
   constexpr int OUT = M * N * NS;
@@ -226,9 +237,95 @@ __device__ __forceinline__ void mm_static(float* __restrict__ C, const float* __
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
   }
-  float* cp = C + s * OFFC + (TM * ti) * LDC + TN * tj;
+  float* cp = C + s * OFFC + (TM * ti) * LDC;
 #pragma unroll
-  for (int i = 0; i < TM; ++i) stv<TN>(cp + i * LDC, acc[i]);
+  for (int i = 0; i < TM; ++i) stv<TN>(cp + i * LDC + swz<CSW>(TM * ti + i, TN * tj), acc[i]);
+}
+
+// ---- tensor-core contractions (mma.sync m16n8k8, TF32 inputs, fp32 accumulate) ----
+// The 8 x 4 FFMA tiles above read 12 floats per lane and k step: 3 LDS.128 = 12 shared-memory
+// wavefronts per 32 FFMA, and the four 1,024-output contractions of the chain were bound by
+// the LSU pipe (88 % of its wavefront peak, profiles/ncu_overlap_r1.csv), not by the FMA pipe.
+// An MMA fragment load touches every operand element once per warp (16 LDS.32 per k step of 8
+// for a 32 x 32 x 8 product).  TF32 has a 10-bit mantissa, the parity bar is 1e-5, so every
+// operand is split x = hi + lo (both TF32) and three MMAs (lo.hi, hi.lo, hi.hi) give products
+// to ~2^-21: "3xTF32".
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// NS slices of C[m][n] = sum_k Xt[k][m] Y[k][n]; Xt rows of LDX floats and Y rows of LDY floats
+// are swizzled (swz<LDX>, swz<LDY>), C is written with swz<CSW>.  OFFX == 0: Xt shared by the slices.
+template <int M, int N, int K, int NS, int LDC, int OFFC, int CSW, int LDX, int OFFX, int LDY, int OFFY>
+__device__ __forceinline__ void mma_static(float* __restrict__ C, const float* __restrict__ Xt,
+                                           const float* __restrict__ Y, int lane) {
+  constexpr int MT = M / 16, NTL = N / 8, KS = K / 8;
+  static_assert(M % 16 == 0 && N % 8 == 0 && K % 8 == 0, "mma tile");
+  const int g = lane >> 2, t = lane & 3;
+  float acc[NS][MT][NTL][4];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[s][mt][nt][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int k0 = 8 * ks + t, k1 = k0 + 4;
+    uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (OFFX != 0 || s == 0) {
+        const float* x0 = Xt + s * OFFX + k0 * LDX;
+        const float* x1 = Xt + s * OFFX + k1 * LDX;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int m = 16 * mt + g;
+          split_tf32(x0[swz<LDX>(k0, m)], ah[mt][0], al[mt][0]);
+          split_tf32(x0[swz<LDX>(k0, m + 8)], ah[mt][1], al[mt][1]);
+          split_tf32(x1[swz<LDX>(k1, m)], ah[mt][2], al[mt][2]);
+          split_tf32(x1[swz<LDX>(k1, m + 8)], ah[mt][3], al[mt][3]);
+        }
+      }
+      const float* y0 = Y + s * OFFY + k0 * LDY;
+      const float* y1 = Y + s * OFFY + k1 * LDY;
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        const int n = 8 * nt + g;
+        uint32_t bh[2], bl[2];
+        split_tf32(y0[swz<LDY>(k0, n)], bh[0], bl[0]);
+        split_tf32(y1[swz<LDY>(k1, n)], bh[1], bl[1]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_tf32(acc[s][mt][nt], al[mt], bh);
+          mma_tf32(acc[s][mt][nt], ah[mt], bl);
+          mma_tf32(acc[s][mt][nt], ah[mt], bh);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        const int r = 16 * mt + g, col = 8 * nt + 2 * t;
+        float* c0 = C + s * OFFC + r * LDC + swz<CSW>(r, col);
+        float* c1 = C + s * OFFC + (r + 8) * LDC + swz<CSW>(r + 8, col);
+        *reinterpret_cast<float2*>(c0) = make_float2(acc[s][mt][nt][0], acc[s][mt][nt][1]);
+        *reinterpret_cast<float2*>(c1) = make_float2(acc[s][mt][nt][2], acc[s][mt][nt][3]);
+      }
 }
 
 template <int NSITE>
@@ -248,7 +345,7 @@ __device__ __forceinline__ void nat_left_step(float* E, float* Tb, const float* 
   __syncwarp();
 }
 
-template <int NSITE>
+template <int NSITE, int CSW = 0>
 __device__ __forceinline__ void nat_right_step(float* R, float* R2, float* Tb, const float* Wt, const float* At,
                                                int lane) {
   constexpr int al = 1 << (10 - NSITE), ar = 1 << (9 - NSITE), Bl = al, Br = ar;
@@ -257,7 +354,7 @@ __device__ __forceinline__ void nat_right_step(float* R, float* R2, float* Tb, c
   mm_static<Br, al, ar, 2, ldTp, Br * ldTp, ldR, 0, ldAt, ar * ldAt>(Tb, R, At, lane);
   __syncwarp();
   // R'[a][B] = sum_(s,B') T'[(s,B')][a] Wt[(s,B')][B]
-  mm_static<al, Bl, 2 * Br, 1, ldWt, 0, ldTp, 0, ldWt, 0>(R2, Tb, Wt, lane);
+  mm_static<al, Bl, 2 * Br, 1, ldWt, 0, ldTp, 0, ldWt, 0, CSW>(R2, Tb, Wt, lane);
   __syncwarp();
 }
 
@@ -270,10 +367,13 @@ inline bool overlap_is_natural(const OverlapParams& P) {
   return true;
 }
 
-template <bool NAT>
+// MODE 0: run-time shapes; 1: natural 32/32 profile, compile-time shapes, FFMA; 2: the same with
+// the three largest contractions on the tensor cores (3xTF32)
+template <int MODE>
 __global__ void __launch_bounds__(256, 1)
 overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_constant__ OverlapFast F,
                     const float* __restrict__ small_w, const float* __restrict__ wc) {
+  constexpr bool NAT = MODE > 0, MMA = MODE == 2;
   extern __shared__ __align__(128) unsigned char smem_ov[];
   float* sW = reinterpret_cast<float*>(smem_ov);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -335,6 +435,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
     } else {
       const int sdx = q / al, a = q - sdx * al;
       d = (sdx * ar + ap) * r4(al) + a;
+      if (MMA && n == c) d = (sdx * ar + ap) * 32 + swz<32>(ap, a);  // fragment operand of G
     }
     tab[e] = (unsigned short)(F.a_off[n] + d);
   }
@@ -361,8 +462,14 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
         const int v = lane + 32 * j;
         if (NAT && v >= 1 && v <= 340) {
           // sites 1..4 of the natural profile keep their layout ([s][a][a'], no row padding):
-          // a straight 128-bit copy, 4 floats further on (site 0 is padded from 4 to 8 floats)
-          *reinterpret_cast<float4*>(As + 4 * v + 4) = pre[j];
+          // a straight 128-bit copy, 4 floats further on (site 0 is padded from 4 to 8 floats);
+          // site 4 (v >= 85) is a fragment operand of the tensor-core path: swizzled rows
+          int dst = 4 * v + 4;
+          if (MMA && v >= 85) {
+            const int i = 4 * v - 340;
+            dst = 344 + (i & ~31) + swz<32>(i >> 5, i & 31);
+          }
+          *reinterpret_cast<float4*>(As + dst) = pre[j];
         } else if (4 * v < stride) {
           const uint2 t = *reinterpret_cast<const uint2*>(tab + 4 * v);
           As[t.x & 0xffff] = pre[j].x;
@@ -387,19 +494,33 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       nat_left_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], lane);
       nat_left_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], lane);
       nat_left_step<3>(E, Tb, sW + F.w_off[3], As + F.a_off[3], lane);
-      nat_left_step<4>(E, Tb, sW + F.w_off[4], As + F.a_off[4], lane);
+      if constexpr (MMA) {
+        // T[(s,a)][B'] (FFMA, K = 16) written swizzled; EL[a'][B'] = sum_(s,a) A4[(s,a)][a'] T[(s,a)][B'] by MMA
+        mm_static<16, 32, 16, 2, 32, 512, 16, 0, 32, 512, 32>(Tb, E, sW + F.w_off[4], lane);
+        __syncwarp();
+        mma_static<32, 32, 32, 1, 32, 0, 32, 32, 0, 32, 0>(E, As + F.a_off[4], Tb, lane);
+        __syncwarp();
+      } else {
+        nat_left_step<4>(E, Tb, sW + F.w_off[4], As + F.a_off[4], lane);
+      }
       nat_right_step<9>(Rb0, Rb1, Tb, sW + F.w_off[9], As + F.a_off[9], lane);
       nat_right_step<8>(Rb1, Rb0, Tb, sW + F.w_off[8], As + F.a_off[8], lane);
       nat_right_step<7>(Rb0, Rb1, Tb, sW + F.w_off[7], As + F.a_off[7], lane);
-      nat_right_step<6>(Rb1, Rb0, Tb, sW + F.w_off[6], As + F.a_off[6], lane);
+      nat_right_step<6, MMA ? 16 : 0>(Rb1, Rb0, Tb, sW + F.w_off[6], As + F.a_off[6], lane);
       float* R = Rb0;
       // hairy site: al = 32, ar = 16, Bl = 32, Br = 16
       const float* At = As + F.a_off[5];  // [s][a'][a]
       float* G = Tb;                      // [s][a][B']
       float* H = Tb + 1024;               // [s][B][B']
-      mm_static<32, 16, 16, 2, 16, 32 * 16, 32, 16 * 32, 16, 0>(G, At, R, lane);
-      __syncwarp();
-      mm_static<32, 16, 32, 2, 16, 32 * 16, 32, 0, 16, 32 * 16>(H, E, G, lane);
+      if constexpr (MMA) {
+        mma_static<32, 16, 16, 2, 16, 512, 16, 32, 512, 16, 0>(G, At, R, lane);
+        __syncwarp();
+        mma_static<32, 16, 32, 2, 16, 512, 0, 32, 0, 16, 512>(H, E, G, lane);
+      } else {
+        mm_static<32, 16, 16, 2, 16, 32 * 16, 32, 16 * 32, 16, 0>(G, At, R, lane);
+        __syncwarp();
+        mm_static<32, 16, 32, 2, 16, 32 * 16, 32, 0, 16, 32 * 16>(H, E, G, lane);
+      }
       __syncwarp();
       // out[l] = sum_(s,B,B') Wc[(s,B,B')][l] H[s][B][B'].  Wc is [(s,B)][B'][l] = 64 rows of 1 KB:
       // lane = (B' mod 8, label quad), so one warp load is 512 contiguous bytes (half a row);
@@ -558,6 +679,10 @@ inline int& overlap_static_shapes() {
   static int v = 1;
   return v;
 }
+inline int& overlap_mma() {
+  static int v = 1;
+  return v;
+}
 
 // Host-side plan; returns false when the shapes do not fit the fast kernel.
 inline bool overlap_fast_plan(const OverlapParams& P, OverlapFast& F) {
@@ -619,18 +744,23 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   const size_t smem = wbytes + tabbytes + (size_t)warps * PER_WARP * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    e = cudaFuncSetAttribute(overlap_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    e = cudaFuncSetAttribute(overlap_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(overlap_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    e = cudaFuncSetAttribute(overlap_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(overlap_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t need = (P.N + warps - 1) / warps;
   const int grid = (int)(need < sms ? need : sms);
-  if (overlap_static_shapes() && overlap_is_natural(P) && F.Spad == 16)
-    overlap_fast_kernel<true><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+  const bool nat = overlap_static_shapes() && overlap_is_natural(P) && F.Spad == 16;
+  if (nat && overlap_mma())
+    overlap_fast_kernel<2><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+  else if (nat)
+    overlap_fast_kernel<1><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   else
-    overlap_fast_kernel<false><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+    overlap_fast_kernel<0><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
