@@ -249,11 +249,14 @@ __device__ __forceinline__ void mm_static(float* __restrict__ C, const float* __
 // An MMA fragment load touches every operand element once per warp (16 LDS.32 per k step of 8
 // for a 32 x 32 x 8 product).  TF32 has a 10-bit mantissa, the parity bar is 1e-5, so every
 // operand is split x = hi + lo (both TF32) and three MMAs (lo.hi, hi.lo, hi.hi) give products
-// to ~2^-21: "3xTF32".
+// to ~2^-20: "3xTF32".
+// hi = x with the mantissa cut to TF32's 10 bits, lo = x - hi (exact).  The tensor core reads
+// only the upper 19 bits of a TF32 operand, so lo is used as it is: its own truncation is an
+// error of 2^-20 |x|.  (cvt.rna.tf32.f32 is emulated with ~5 instructions on sm_100a; two of
+// them per operand element were 40 % of the kernel's instructions.)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
