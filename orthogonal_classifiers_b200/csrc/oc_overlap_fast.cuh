@@ -24,6 +24,9 @@ constexpr int kOvE = 1024;           // 32 x 32 environment
 constexpr int kOvT = 2048;           // 2 x 32 x 32 scratch
 constexpr int kOvR = 256;            // 16 x 16 right environment (x2, ping-pong)
 constexpr int kOvPre = 22;           // float4 prefetch registers per lane: images of <= 22*128 floats
+// floats of per-warp scratch; the +4 puts the 8 warps' buffers on different banks (the CTA-wide
+// label sums read element k of all 8 H buffers in one fragment load)
+constexpr int kOvPerWarp = kOvMaxA + kOvE + kOvT + 2 * kOvR + 4;
 
 __host__ __device__ inline int r4(int x) { return (x + 3) & ~3; }
 
@@ -250,13 +253,15 @@ __device__ __forceinline__ void mm_static(float* __restrict__ C, const float* __
 // for a 32 x 32 x 8 product).  TF32 has a 10-bit mantissa, the parity bar is 1e-5, so every
 // operand is split x = hi + lo (both TF32) and three MMAs (lo.hi, hi.lo, hi.hi) give products
 // to ~2^-20: "3xTF32".
-// hi = x with the mantissa cut to TF32's 10 bits, lo = x - hi (exact).  The tensor core reads
-// only the upper 19 bits of a TF32 operand, so lo is used as it is: its own truncation is an
-// error of 2^-20 |x|.  (cvt.rna.tf32.f32 is emulated with ~5 instructions on sm_100a; two of
-// them per operand element were 40 % of the kernel's instructions.)
+// hi = x with the mantissa cut to TF32's 10 bits, lo = x - hi (exact, <= 13 significant bits).
+// The tensor core reads only the upper 19 bits of a TF32 operand, so adding half an ulp of that
+// format to lo's bit pattern makes the hardware's truncation a rounding to nearest: the
+// representation error of x is <= 2^-21 |x| and unbiased.  (cvt.rna.tf32.f32 is emulated with
+// ~5 instructions on sm_100a; two of them per operand element were 40 % of the kernel's
+// instructions.)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
+  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -380,7 +385,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
   extern __shared__ __align__(128) unsigned char smem_ov[];
   float* sW = reinterpret_cast<float*>(smem_ov);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr int PER_WARP = kOvMaxA + kOvE + kOvT + 2 * kOvR;
+  constexpr int PER_WARP = kOvPerWarp;
   float* wbase = sW + ((F.small_w_total + 31) & ~31) + (size_t)warp * PER_WARP;
   float* As = wbase;
   float* Eb = As + kOvMaxA;
@@ -455,9 +460,13 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       if (4 * v < stride) pre[j] = __ldcs(src + v);
     }
   };
-  int64_t img = (int64_t)blockIdx.x * nwarps + warp;
-  if (vec && img < P.N) prefetch(img);
-  for (; img < P.N; img += (int64_t)gridDim.x * nwarps) {
+  if (vec && (int64_t)blockIdx.x * nwarps + warp < P.N) prefetch((int64_t)blockIdx.x * nwarps + warp);
+  // the trip count is per CTA (the tensor-core label sums below are CTA-wide); a warp whose image
+  // index runs past N only takes part in the barriers
+  for (int64_t base = (int64_t)blockIdx.x * nwarps; base < P.N; base += (int64_t)gridDim.x * nwarps) {
+    const int64_t img = base + warp;
+    const bool valid = img < P.N;
+    if (valid) {
     const float* mps = reinterpret_cast<const float*>(P.mps) + (size_t)img * P.mps_stride;
     if (vec) {
 #pragma unroll
@@ -525,6 +534,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
         mm_static<32, 16, 32, 2, 16, 32 * 16, 32, 0, 16, 32 * 16>(H, E, G, lane);
       }
       __syncwarp();
+      if constexpr (!MMA) {
       // out[l] = sum_(s,B,B') Wc[(s,B,B')][l] H[s][B][B'].  Wc is [(s,B)][B'][l] = 64 rows of 1 KB:
       // lane = (B' mod 8, label quad), so one warp load is 512 contiguous bytes (half a row);
       // 32 loads in flight per lane hide the L2 latency (Wc, 64 KB, does not fit the L1 left
@@ -572,6 +582,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
         }
         if (lane == 0) P.argmax[img] = besti;
       }
+      }  // !MMA
     } else {
     // ---- left sweep.  State Et[B][a] (ld r4(a)); the last step leaves EL[a][B] ----
     float* E = Eb;
@@ -675,6 +686,63 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
     }
     }  // !NAT
     __syncwarp();
+    }  // valid
+    if constexpr (MMA) {
+      // ---- label sums of the CTA's 8 images as ONE tensor-core product:
+      //      out[l][i] = sum_r Wc[r][l] H_i[r],  r = (s,B,B') < 1024: M = 16 labels, N = 8 images,
+      //      warp w takes r in [128 w, 128 w + 128).  Wc (64 KB) is read from L2 once per 8 images
+      //      instead of once per image (it was 6 TB/s of L2 traffic and a quarter of the samples).
+      __syncthreads();  // every warp's H is in its scratch
+      {
+        const int g = lane >> 2, t = lane & 3;
+        const float* hb = sW + ((F.small_w_total + 31) & ~31) + (size_t)g * PER_WARP + kOvMaxA + kOvE + 1024 +
+                          128 * warp;            // H of image g (warp g), this warp's rows
+        const float* wcw = wc + (size_t)(128 * warp) * 16;
+        float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+          const int k0 = 8 * ks + t, k1 = k0 + 4;
+          uint32_t ah[4], al[4], bh[2], bl[2];
+          split_tf32(__ldg(wcw + k0 * 16 + g), ah[0], al[0]);
+          split_tf32(__ldg(wcw + k0 * 16 + g + 8), ah[1], al[1]);
+          split_tf32(__ldg(wcw + k1 * 16 + g), ah[2], al[2]);
+          split_tf32(__ldg(wcw + k1 * 16 + g + 8), ah[3], al[3]);
+          split_tf32(hb[k0], bh[0], bl[0]);
+          split_tf32(hb[k1], bh[1], bl[1]);
+          mma_tf32(acc4, al, bh);
+          mma_tf32(acc4, ah, bl);
+          mma_tf32(acc4, ah, bh);
+        }
+        // partial sums [label][image] into this warp's (free) G scratch
+        float* red = Tb;
+        *reinterpret_cast<float2*>(red + g * 8 + 2 * t) = make_float2(acc4[0], acc4[1]);
+        *reinterpret_cast<float2*>(red + (g + 8) * 8 + 2 * t) = make_float2(acc4[2], acc4[3]);
+      }
+      __syncthreads();
+      {
+        // warp = image: lane l < 16 adds the 8 partial sums of label l
+        float v = 0.f;
+        if (lane < 16) {
+          const float* rb = sW + ((F.small_w_total + 31) & ~31) + kOvMaxA + kOvE + lane * 8 + warp;
+#pragma unroll
+          for (int w2 = 0; w2 < 8; ++w2) v += rb[(size_t)w2 * PER_WARP];
+        }
+        v = fabsf(v);
+        if (valid && lane < 16) reinterpret_cast<float*>(P.overlaps)[(size_t)img * 16 + lane] = v;
+        if (P.argmax) {
+          float best = lane < 16 ? v : -1.f;
+          int besti = lane;
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) {
+            const float ob = __shfl_xor_sync(FULL, best, o);
+            const int oi = __shfl_xor_sync(FULL, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+          }
+          if (valid && lane == 0) P.argmax[img] = besti;
+        }
+      }
+      __syncthreads();  // the partial sums are read before anyone's next G overwrites them
+    }
   }
 }
 
@@ -739,7 +807,7 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   overlap_prep_kernel<float><<<1, 1024, 0, st>>>(reinterpret_cast<const float*>(P.clf), P, F, small_w, wc);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  constexpr int PER_WARP = kOvMaxA + kOvE + kOvT + 2 * kOvR;
+  constexpr int PER_WARP = kOvPerWarp;
   const size_t wbytes = (size_t)((F.small_w_total + 31) & ~31) * 4;
   const size_t tabbytes = (((size_t)P.mps_stride * 2 + 15) & ~(size_t)15) + 16;
   int warps = 8;
@@ -758,7 +826,7 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   const int64_t need = (P.N + warps - 1) / warps;
   const int grid = (int)(need < sms ? need : sms);
   const bool nat = overlap_static_shapes() && overlap_is_natural(P) && F.Spad == 16;
-  if (nat && overlap_mma())
+  if (nat && overlap_mma() && warps == 8)
     overlap_fast_kernel<2><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   else if (nat)
     overlap_fast_kernel<1><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
