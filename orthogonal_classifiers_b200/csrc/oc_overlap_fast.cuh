@@ -460,6 +460,16 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       if (4 * v < stride) pre[j] = __ldcs(src + v);
     }
   };
+  // the same in four bursts (natural profile): 22 back-to-back 512-byte warp loads from eight warps
+  // ran into the load/store unit's queue limit (lg_throttle, a fifth of the samples)
+  auto prefetch_part = [&](int64_t im, int part) {
+    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.mps) + (size_t)im * stride);
+#pragma unroll
+    for (int j = 0; j < kOvPre; ++j) {
+      const int v = lane + 32 * j;
+      if ((j * 4) / kOvPre == part && 4 * v < stride) pre[j] = __ldcs(src + v);
+    }
+  };
   if (vec && (int64_t)blockIdx.x * nwarps + warp < P.N) prefetch((int64_t)blockIdx.x * nwarps + warp);
   // the trip count is per CTA (the tensor-core label sums below are CTA-wide); a warp whose image
   // index runs past N only takes part in the barriers
@@ -491,7 +501,10 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
         }
       }
       const int64_t nxt = img + (int64_t)gridDim.x * nwarps;
-      if (nxt < P.N) prefetch(nxt);  // in flight during this image's contractions
+      if (nxt < P.N) {  // in flight during this image's contractions
+        if constexpr (NAT) prefetch_part(nxt, 0);
+        else prefetch(nxt);
+      }
     } else {
       for (int e = lane; e < stride; e += 32) As[tab[e]] = __ldg(mps + e);
     }
@@ -506,6 +519,8 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       nat_left_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], lane);
       nat_left_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], lane);
       nat_left_step<3>(E, Tb, sW + F.w_off[3], As + F.a_off[3], lane);
+      const int64_t nxt_img = img + (int64_t)gridDim.x * nwarps;
+      if (vec && nxt_img < P.N) prefetch_part(nxt_img, 1);
       if constexpr (MMA) {
         // T[(s,a)][B'] (FFMA, K = 16) written swizzled; EL[a'][B'] = sum_(s,a) A4[(s,a)][a'] T[(s,a)][B'] by MMA
         mm_static<16, 32, 16, 2, 32, 512, 16, 0, 32, 512, 32>(Tb, E, sW + F.w_off[4], lane);
@@ -515,10 +530,12 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       } else {
         nat_left_step<4>(E, Tb, sW + F.w_off[4], As + F.a_off[4], lane);
       }
+      if (vec && nxt_img < P.N) prefetch_part(nxt_img, 2);
       nat_right_step<9>(Rb0, Rb1, Tb, sW + F.w_off[9], As + F.a_off[9], lane);
       nat_right_step<8>(Rb1, Rb0, Tb, sW + F.w_off[8], As + F.a_off[8], lane);
       nat_right_step<7>(Rb0, Rb1, Tb, sW + F.w_off[7], As + F.a_off[7], lane);
       nat_right_step<6, MMA ? 16 : 0>(Rb1, Rb0, Tb, sW + F.w_off[6], As + F.a_off[6], lane);
+      if (vec && nxt_img < P.N) prefetch_part(nxt_img, 3);
       float* R = Rb0;
       // hairy site: al = 32, ar = 16, Bl = 32, Br = 16
       const float* At = As + F.a_off[5];  // [s][a'][a]
