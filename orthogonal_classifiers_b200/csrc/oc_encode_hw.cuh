@@ -1065,8 +1065,7 @@ hw_row4q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
   }
   __syncwarp();
   // vectors of 2 gs elements: the rotation cost is proportional to the padded length
-  if (gs <= 8) q4_tail<8>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
-  else if (gs <= 10) q4_tail<10>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
+  if (gs <= 10) q4_tail<10>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
   else q4_tail<kQ4NE>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
 }
 
