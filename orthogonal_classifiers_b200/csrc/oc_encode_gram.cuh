@@ -338,7 +338,11 @@ __device__ __forceinline__ int jacobi_groups(u64 (&T)[16], u64 (&S)[16], float& 
       for (int e = 0; e < 8; ++e) T[e] = shfl2(T[e], src_up);
       nT = __shfl_sync(FULL, nR, src_up);
       {
+#ifdef OC_TRACK_LOST
         const unsigned lostmask = __ballot_sync(FULL, lostf);
+#else
+        const unsigned lostmask = 0u;
+#endif
         if (lostmask) {
           const float fT = dot16<0, 8>(T, T), fS = dot16<0, 8>(S, S);
           if (lostmask & gmask) {

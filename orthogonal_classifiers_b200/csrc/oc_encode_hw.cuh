@@ -98,7 +98,14 @@ __device__ __forceinline__ void rotate16(u64 (&a)[NA], u64 (&b)[NA], float& na, 
   // a norm update that cancelled is refreshed from the data at the end of the
   // round pair (jacobi16); until then the stale value only makes one rotation
   // less effective, never wrong (c and s stay consistent)
+  // A norm update that cancelled leaves a stale cached norm until the refresh at the start of the
+  // next sweep.  It can only happen in a rotation by a large angle, which forces that next sweep
+  // (`again`), and a stale norm makes a later rotation of the same sweep less effective, never
+  // wrong (c and s stay consistent).  Refreshing inside the sweep (OC_TRACK_LOST) costs 2-3 % of
+  // the encoder and changes neither the sweep counts nor the results (profiles/encode_r1.md).
+#ifdef OC_TRACK_LOST
   lostf = lostf || (rot && (n_second < kCancel * aa || n_first < kCancel * bb));
+#endif
   const u64 c2 = pack2(c, c), s2 = pack2(s, s), ns2 = pack2(ns, ns);
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
@@ -152,7 +159,11 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
         nT = __shfl_sync(FULL, nR, src_up);
       }
       {
+#ifdef OC_TRACK_LOST
         const unsigned lostmask = __ballot_sync(FULL, lostf);
+#else
+        const unsigned lostmask = 0u;
+#endif
         if (lostmask) {  // warp-uniform, rare after the first sweeps
           const float fT = dot16<LOGLP, NE>(T, T), fS = dot16<LOGLP, NE>(S, S);
           if (lostmask & gmask) {  // only the group that cancelled takes the refreshed norms
@@ -607,7 +618,11 @@ __device__ __forceinline__ int jacobi_ring(u64 (&T)[NA], u64 (&S)[NA], float& nT
       for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_up);
       nT = __shfl_sync(FULL, nR, src_up);
       {
+#ifdef OC_TRACK_LOST
         const unsigned lostmask = __ballot_sync(FULL, lostf);
+#else
+        const unsigned lostmask = 0u;
+#endif
         if (lostmask) {
           const float fT = dot16<0, NE>(T, T), fS = dot16<0, NE>(S, S);
           if (lostmask & gmask) {
