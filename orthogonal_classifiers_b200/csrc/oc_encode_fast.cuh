@@ -229,7 +229,8 @@ __device__ __forceinline__ int jacobi_regs(u64 (&T)[E2], u64 (&S)[E2], u64 (&UT)
       }
     }
     ++sweeps;
-    if (M == 1 || mlive == 1) break;  // one rotation orthogonalises two vectors exactly
+    // (two vectors: one rotation orthogonalises them in exact arithmetic only; with graded norms the
+    //  fp32 rotation leaves cos ~ 1e-4, so the usual criterion decides here as well)
     if (!__any_sync(FULL, again)) break;
   }
   return sweeps;

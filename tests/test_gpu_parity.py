@@ -271,6 +271,35 @@ def test_encoding_does_not_depend_on_batch_composition(gpu_lib):
         np.testing.assert_array_equal(x, y)
 
 
+def test_scale_invariance_and_low_contrast(gpu_lib):
+    """The MPS is unit norm (the final 1x1 S.V is dropped), so the overlaps must
+    not depend on the pixel scale: every threshold in the encoder is relative.
+    Also images with almost-dependent rows (low contrast on a constant offset)."""
+    imgs = synthetic_images(200, seed=37).astype(np.float64)
+    clf = random_classifier(10, 32, centre=5, seed=8)
+    W = oracle.dense_classifier(clf)
+    ref = oracle.overlaps_dense(imgs, W)
+    for scale in (1e-3, 1.0, 255.0, 1e3):
+        ov, _ = gpu_lib.classify((imgs * scale).astype(np.float32), clf, 32)
+        assert np.abs(ov - ref).max() <= 1e-5 * ref.max(), scale
+    # graded spectra: sigma_2 / sigma_1 ~ 1e-3 .. 1e-4 and singular values down to the 1e-6 floor.
+    # (Caught a single fp32 rotation at step 8 leaving cos ~ 1e-4 between graded columns, and a
+    # one-pass polish leaving 1e-3 between columns with sigma < 3e-5 sigma_max.)  At contrast 1e-3
+    # fp32 pixels themselves carry the strokes to only ~6e-5, hence the looser bound there.
+    for contrast, tol in ((1e-1, 1e-5), (1e-2, 1e-5), (1e-3, 2e-5)):
+        low = (0.5 + contrast * imgs).astype(np.float32)
+        ref_low = oracle.overlaps_dense(low.astype(np.float64), W)
+        ov, _ = gpu_lib.classify(low, clf, 32)
+        assert np.abs(ov - ref_low).max() <= tol * ref_low.max(), contrast
+        batch = gpu_lib.encode_images(low[:16], 32)
+        for i in range(16):
+            for n, A in enumerate(batch.sites_numpy(i)):
+                M = A.reshape(-1, A.shape[2]).astype(np.float64)
+                G = M.T @ M
+                nz = np.diag(G) > 0.5
+                assert np.abs(G[np.ix_(nz, nz)] - np.eye(nz.sum())).max() < 20 * TOL["f32"], (contrast, i, n)
+
+
 def test_chunk_boundary_of_the_encoder(gpu_lib):
     """The encoder works in chunks of 131,072 images (workspace and sort lists are
     per chunk): images on both sides of the boundary must come out as they do in
