@@ -300,6 +300,43 @@ def test_scale_invariance_and_low_contrast(gpu_lib):
                 assert np.abs(G[np.ix_(nz, nz)] - np.eye(nz.sum())).max() < 20 * TOL["f32"], (contrast, i, n)
 
 
+def test_image_families(gpu_lib):
+    """Inputs the MNIST-shaped synthetic strokes do not cover: flat spectra (white
+    noise), exactly rank-deficient patterns (ramps, checkerboards, blocks), almost
+    rank-1 images (constant + 1e-4 noise), twelve decades of dynamic range."""
+    rng = np.random.default_rng(5)
+    n = 96
+    yy, xx = np.mgrid[0:28, 0:28]
+    fam = {
+        "white noise": rng.random((n, 784)),
+        "sparse pixels": (rng.random((n, 784)) < 0.01) * rng.random((n, 784)),
+        "ramps": np.stack([((a * xx + b * yy) % 28 / 27.0).reshape(-1) for a, b in rng.integers(0, 5, (n, 2))]),
+        "checker": np.stack([(((xx // p) + (yy // q)) % 2).reshape(-1).astype(float)
+                             for p, q in rng.integers(1, 8, (n, 2))]),
+        "blocks": np.stack([((xx > a) & (xx < a + 9) & (yy > b) & (yy < b + 6)).reshape(-1).astype(float)
+                            for a, b in rng.integers(0, 18, (n, 2))]),
+        "const + noise": 0.7 + 1e-4 * rng.standard_normal((n, 784)),
+        "huge range": rng.random((n, 784)) ** 12,
+    }
+    clf = random_classifier(10, 32, centre=5, seed=9)
+    W = oracle.dense_classifier(clf)
+    for name, imgs in fam.items():
+        x32 = imgs.astype(np.float32)
+        ref = oracle.overlaps_dense(x32.astype(np.float64), W)
+        ov, am = gpu_lib.classify(x32, clf, 32)
+        assert np.abs(ov - ref).max() <= 1e-5 * ref.max(), name
+        srt = np.sort(ref, axis=1)
+        tie = (srt[:, -1] - srt[:, -2]) < 1e-5 * ref.max()
+        assert np.all((am == ref.argmax(1)) | tie), name
+        batch = gpu_lib.encode_images(x32[:8], 32)
+        for i in range(8):
+            for A in batch.sites_numpy(i):
+                M = A.reshape(-1, A.shape[2]).astype(np.float64)
+                G = M.T @ M
+                nz = np.diag(G) > 0.5
+                assert np.abs(G[np.ix_(nz, nz)] - np.eye(nz.sum())).max() < 20 * TOL["f32"], name
+
+
 def test_chunk_boundary_of_the_encoder(gpu_lib):
     """The encoder works in chunks of 131,072 images (workspace and sort lists are
     per chunk): images on both sides of the boundary must come out as they do in
