@@ -115,7 +115,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = 256 * cores
+    # ~1.5 s of work per step on 16 cores: large enough that starting the worker pool (every
+    # step) does not dominate, small enough that K steps end within a few minutes
+    per_step = 2048 * cores
     for _ in range(args.warmup):
         cpu_reference(min(per_step, 64 * cores), cores)
     t0 = time.perf_counter()
