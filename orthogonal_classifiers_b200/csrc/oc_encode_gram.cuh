@@ -39,12 +39,14 @@ constexpr double kCholFloor = 1e-13;  // pivots below this fraction of trace(G) 
 
 // ---- pixels: four consecutive amplitudes i .. i+3 of the tail-padded image ----
 struct PixRow {
+  const float* lut;  // MODE 2: 256 floats k / 255.f in shared memory (else unused)
   const void* p;
   int dtype, n_pix;
   bool vec, vec8;
 };
 __device__ __forceinline__ PixRow pix_row(const EncodeParams& P, int64_t img) {
   PixRow r;
+  r.lut = nullptr;
   const char* src = reinterpret_cast<const char*>(P.images);
   const int esz = P.in_dtype == 0 ? 4 : (P.in_dtype == 1 ? 8 : 1);
   r.p = src + (size_t)img * P.ld * esz;
@@ -80,11 +82,25 @@ __device__ __forceinline__ float4 pix4m(const PixRow& r, int i) {
     if (i < r.n_pix) v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r.p) + i));
     return v;
   } else if constexpr (MODE == 2) {
+    // table lookup instead of four I2F + fp32 divisions (same bits: the table holds float(k) / 255.f)
     uchar4 u = make_uchar4(0, 0, 0, 0);
     if (i < r.n_pix) u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(r.p) + i));
+    if (r.lut) return make_float4(r.lut[u.x], r.lut[u.y], r.lut[u.z], r.lut[u.w]);
     return make_float4(float(u.x) / 255.f, float(u.y) / 255.f, float(u.z) / 255.f, float(u.w) / 255.f);
   } else {
     return pix4(r, i);
+  }
+}
+// fills the k / 255.f table of a CTA (all threads call it; MODE 2 only)
+template <int MODE>
+__device__ __forceinline__ const float* pix_lut() {
+  if constexpr (MODE == 2) {
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = float(i) / 255.f;
+    __syncthreads();
+    return lut;
+  } else {
+    return nullptr;
   }
 }
 inline int pix_mode(const EncodeParams& P) {
@@ -121,9 +137,11 @@ __global__ void __launch_bounds__(kHwWarps * 32, 3) gram_kernel(const __grid_con
   const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
   const bool valid = img < P.N;
   double* Xt = smem_d + (size_t)(warp * 2 + h) * kXtDoubles;
+  const float* lut = pix_lut<MODE>();
   // stage: coalesced loads (all 16 in flight), then fp64 stores Xt[k][row]
   {
-    const PixRow src = pix_row(P, valid ? img : 0);
+    PixRow src = pix_row(P, valid ? img : 0);
+    src.lut = lut;
     float4 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -519,7 +537,7 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
   __syncwarp();
 
   // first rows of X_3 for the Psi_4 product: in flight during the A_n products
-  const PixRow src = pix_row(P, im);
+  const PixRow src = pix_row(P, im);  // (no table here: 1 KB more would cost the fourth CTA per SM)
   const int rows_live = (P.n_pix + 63) >> 6;
   float4 xa[4];
 #pragma unroll
