@@ -537,7 +537,18 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
   __syncwarp();
 
   // first rows of X_3 for the Psi_4 product: in flight during the A_n products
-  const PixRow src = pix_row(P, im);  // (no table here: 1 KB more would cost the fourth CTA per SM)
+  PixRow src = pix_row(P, im);
+  if constexpr (MODE == 2) {
+    // k / 255.f table of this WARP in the (now dead) fp32 L-column buffer of its first image:
+    // 1 KB more of CTA-wide shared memory would cost the fourth CTA per SM
+    float* lutw = reinterpret_cast<float*>(smem_b + (size_t)(warp * 2) * kHeadSmemBytes + kGsDoubles * 8 +
+                                           kLsDoubles * 8);
+    static_assert(kLfFloats >= 256, "table does not fit the L-column buffer");
+#pragma unroll
+    for (int i = lane; i < 256; i += 32) lutw[i] = float(i) / 255.f;
+    __syncwarp();
+    src.lut = lutw;
+  }
   const int rows_live = (P.n_pix + 63) >> 6;
   float4 xa[4];
 #pragma unroll
