@@ -336,6 +336,67 @@ __device__ __forceinline__ void mma_static(float* __restrict__ C, const float* _
       }
 }
 
+// Two independent contractions of the SAME static shape, one per half-warp.  Left-sweep step n and
+// right-sweep step 9 - n of the natural profile are mirror images (same M, N, K and strides), and
+// each is a chain of short dependent phases: running them side by side halves the number of
+// phases (16 -> 8 for sites 0-3 / 9-6).  CSW1: output swizzle of the second problem.
+template <int M, int N, int K, int NS, int LDC, int OFFC, int LDX, int OFFX, int LDY, int OFFY, int CSW1 = 0>
+__device__ __forceinline__ void mm_static_pair(float* __restrict__ C0, const float* __restrict__ X0,
+                                               const float* __restrict__ Y0, float* __restrict__ C1,
+                                               const float* __restrict__ X1, const float* __restrict__ Y1,
+                                               int lane) {
+  constexpr int OUT = M * N * NS;
+  constexpr int TM = OUT >= 256 ? 4 : (OUT >= 64 ? 2 : 1);
+  constexpr int TN = TM;
+  static_assert(M % TM == 0 && N % TN == 0, "tile does not divide the shape");
+  constexpr int tm = M / TM, tn = N / TN, per = tm * tn, NT = per * NS;
+  static_assert(NT <= 16, "more tiles than lanes of a half-warp");
+  const int h = lane >> 4, l = lane & 15;
+  if (NT < 16 && l >= NT) return;
+  float* C = h ? C1 : C0;
+  const float* Xt = h ? X1 : X0;
+  const float* Y = h ? Y1 : Y0;
+  const int s = l / per, t = l % per;
+  const int tj = t / tm, ti = t % tm;
+  const float* xp = Xt + s * OFFX + TM * ti;
+  const float* yp = Y + s * OFFY + TN * tj;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+#pragma unroll(K <= 8 ? K : 8)
+  for (int k = 0; k < K; ++k) {
+    float xv[TM], yv[TN];
+    ldv<TM>(xv, xp + k * LDX);
+    ldv<TN>(yv, yp + k * LDY);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+  }
+  float* cp = C + s * OFFC + (TM * ti) * LDC;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int col = h ? swz<CSW1>(TM * ti + i, TN * tj) : TN * tj;
+    stv<TN>(cp + i * LDC + col, acc[i]);
+  }
+}
+
+// left step n (sites 0..3) and right step 9 - n side by side; R ping-pongs between Rcur and Rnext
+template <int NSITE, int CSW1 = 0>
+__device__ __forceinline__ void nat_pair_step(float* E, float* Tb, const float* W, const float* A, const float* Rcur,
+                                              float* Rnext, const float* Wt, const float* At, int lane) {
+  constexpr int al = 1 << NSITE, ar = 2 << NSITE, Bl = al, Br = ar;
+  constexpr int ldE = (al + 3) & ~3, ldW = (Br + 3) & ~3, ldA = (ar + 3) & ~3, ldT = ldW;
+  // T[(s,a)][B'] = sum_B Et[B][a] W[s][B][B']   ||   T'[s][B'][a] = sum_a' R[a'][B'] At[s][a'][a]
+  mm_static_pair<al, Br, Bl, 2, ldT, al * ldT, ldE, 0, ldW, Bl * ldW>(Tb, E, W, Tb + 1024, Rcur, At, lane);
+  __syncwarp();
+  // Et'[B'][a'] = sum_(s,a) T[(s,a)][B'] A[(s,a)][a']   ||   R'[a][B] = sum_(s,B') T'[(s,B')][a] Wt[(s,B')][B]
+  mm_static_pair<Br, ar, 2 * al, 1, ldA, 0, ldT, 0, ldA, 0, CSW1>(E, Tb, A, Rnext, Tb + 1024, Wt, lane);
+  __syncwarp();
+}
+
 template <int NSITE>
 __device__ __forceinline__ void nat_left_step(float* E, float* Tb, const float* W, const float* A, int lane) {
   constexpr int al = 1 << NSITE, ar = 2 << NSITE, Bl = al, Br = ar;
@@ -515,26 +576,34 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       float* E = Eb;
       if (lane == 0) { E[0] = 1.f; Rb0[0] = 1.f; }
       __syncwarp();
-      nat_left_step<0>(E, Tb, sW + F.w_off[0], As + F.a_off[0], lane);
-      nat_left_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], lane);
-      nat_left_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], lane);
-      nat_left_step<3>(E, Tb, sW + F.w_off[3], As + F.a_off[3], lane);
       const int64_t nxt_img = img + (int64_t)gridDim.x * nwarps;
-      if (vec && nxt_img < P.N) prefetch_part(nxt_img, 1);
       if constexpr (MMA) {
+        // sites 0..3 and 9..6 side by side (one half-warp each), then site 4
+        nat_pair_step<0>(E, Tb, sW + F.w_off[0], As + F.a_off[0], Rb0, Rb1, sW + F.w_off[9], As + F.a_off[9], lane);
+        nat_pair_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], Rb1, Rb0, sW + F.w_off[8], As + F.a_off[8], lane);
+        if (vec && nxt_img < P.N) prefetch_part(nxt_img, 1);
+        nat_pair_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], Rb0, Rb1, sW + F.w_off[7], As + F.a_off[7], lane);
+        nat_pair_step<3, 16>(E, Tb, sW + F.w_off[3], As + F.a_off[3], Rb1, Rb0, sW + F.w_off[6], As + F.a_off[6],
+                             lane);
+        if (vec && nxt_img < P.N) prefetch_part(nxt_img, 2);
         // T[(s,a)][B'] (FFMA, K = 16) written swizzled; EL[a'][B'] = sum_(s,a) A4[(s,a)][a'] T[(s,a)][B'] by MMA
         mm_static<16, 32, 16, 2, 32, 512, 16, 0, 32, 512, 32>(Tb, E, sW + F.w_off[4], lane);
         __syncwarp();
         mma_static<32, 32, 32, 1, 32, 0, 32, 32, 0, 32, 0>(E, As + F.a_off[4], Tb, lane);
         __syncwarp();
       } else {
+        nat_left_step<0>(E, Tb, sW + F.w_off[0], As + F.a_off[0], lane);
+        nat_left_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], lane);
+        nat_left_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], lane);
+        nat_left_step<3>(E, Tb, sW + F.w_off[3], As + F.a_off[3], lane);
+        if (vec && nxt_img < P.N) prefetch_part(nxt_img, 1);
         nat_left_step<4>(E, Tb, sW + F.w_off[4], As + F.a_off[4], lane);
+        if (vec && nxt_img < P.N) prefetch_part(nxt_img, 2);
+        nat_right_step<9>(Rb0, Rb1, Tb, sW + F.w_off[9], As + F.a_off[9], lane);
+        nat_right_step<8>(Rb1, Rb0, Tb, sW + F.w_off[8], As + F.a_off[8], lane);
+        nat_right_step<7>(Rb0, Rb1, Tb, sW + F.w_off[7], As + F.a_off[7], lane);
+        nat_right_step<6>(Rb1, Rb0, Tb, sW + F.w_off[6], As + F.a_off[6], lane);
       }
-      if (vec && nxt_img < P.N) prefetch_part(nxt_img, 2);
-      nat_right_step<9>(Rb0, Rb1, Tb, sW + F.w_off[9], As + F.a_off[9], lane);
-      nat_right_step<8>(Rb1, Rb0, Tb, sW + F.w_off[8], As + F.a_off[8], lane);
-      nat_right_step<7>(Rb0, Rb1, Tb, sW + F.w_off[7], As + F.a_off[7], lane);
-      nat_right_step<6, MMA ? 16 : 0>(Rb1, Rb0, Tb, sW + F.w_off[6], As + F.a_off[6], lane);
       if (vec && nxt_img < P.N) prefetch_part(nxt_img, 3);
       float* R = Rb0;
       // hairy site: al = 32, ar = 16, Bl = 32, Br = 16
