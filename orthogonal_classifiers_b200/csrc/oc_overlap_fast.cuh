@@ -42,7 +42,7 @@ struct OverlapFast {
 // ---- classifier re-layout (one small launch per overlap call) --------------
 template <typename TIN>
 __global__ void overlap_prep_kernel(const TIN* __restrict__ clf, OverlapParams P, OverlapFast F,
-                                    float* __restrict__ small_w, float* __restrict__ wc) {
+                                    float* __restrict__ small_w, float* __restrict__ wc, int swz_site = -1) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int i = tid; i < F.small_w_total; i += nth) small_w[i] = 0.f;
   for (int64_t i = tid; i < F.wc_elems; i += nth) wc[i] = 0.f;
@@ -62,7 +62,9 @@ __global__ void overlap_prep_kernel(const TIN* __restrict__ clf, OverlapParams P
       const int ld = r4(Br);
       for (int i = tid; i < 2 * Bl * Br; i += nth) {
         const int bp = i % Br, sb = i / Br;  // sb = s*Bl + b
-        small_w[F.w_off[n] + (int64_t)sb * ld + bp] = (float)W[i];
+        // swz_site: this site is a tensor-core fragment operand (rows of 32): bank swizzle, see swz<32>
+        const int col = n == swz_site ? (bp ^ ((sb & 3) << 3)) : bp;
+        small_w[F.w_off[n] + (int64_t)sb * ld + col] = (float)W[i];
       }
     } else {
       const int ld = r4(Bl);  // transposed: [s][B'][B]
@@ -340,7 +342,8 @@ __device__ __forceinline__ void mma_static(float* __restrict__ C, const float* _
 // right-sweep step 9 - n of the natural profile are mirror images (same M, N, K and strides), and
 // each is a chain of short dependent phases: running them side by side halves the number of
 // phases (16 -> 8 for sites 0-3 / 9-6).  CSW1: output swizzle of the second problem.
-template <int M, int N, int K, int NS, int LDC, int OFFC, int LDX, int OFFX, int LDY, int OFFY, int CSW1 = 0>
+template <int M, int N, int K, int NS, int LDC, int OFFC, int LDX, int OFFX, int LDY, int OFFY, int CSW1 = 0,
+          int CSW0 = 0>
 __device__ __forceinline__ void mm_static_pair(float* __restrict__ C0, const float* __restrict__ X0,
                                                const float* __restrict__ Y0, float* __restrict__ C1,
                                                const float* __restrict__ X1, const float* __restrict__ Y1,
@@ -378,13 +381,13 @@ __device__ __forceinline__ void mm_static_pair(float* __restrict__ C0, const flo
   float* cp = C + s * OFFC + (TM * ti) * LDC;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
-    const int col = h ? swz<CSW1>(TM * ti + i, TN * tj) : TN * tj;
+    const int col = h ? swz<CSW1>(TM * ti + i, TN * tj) : swz<CSW0>(TM * ti + i, TN * tj);
     stv<TN>(cp + i * LDC + col, acc[i]);
   }
 }
 
 // left step n (sites 0..3) and right step 9 - n side by side; R ping-pongs between Rcur and Rnext
-template <int NSITE, int CSW1 = 0>
+template <int NSITE, int CSW1 = 0, int CSW0 = 0>
 __device__ __forceinline__ void nat_pair_step(float* E, float* Tb, const float* W, const float* A, const float* Rcur,
                                               float* Rnext, const float* Wt, const float* At, int lane) {
   constexpr int al = 1 << NSITE, ar = 2 << NSITE, Bl = al, Br = ar;
@@ -393,7 +396,7 @@ __device__ __forceinline__ void nat_pair_step(float* E, float* Tb, const float* 
   mm_static_pair<al, Br, Bl, 2, ldT, al * ldT, ldE, 0, ldW, Bl * ldW>(Tb, E, W, Tb + 1024, Rcur, At, lane);
   __syncwarp();
   // Et'[B'][a'] = sum_(s,a) T[(s,a)][B'] A[(s,a)][a']   ||   R'[a][B] = sum_(s,B') T'[(s,B')][a] Wt[(s,B')][B]
-  mm_static_pair<Br, ar, 2 * al, 1, ldA, 0, ldT, 0, ldA, 0, CSW1>(E, Tb, A, Rnext, Tb + 1024, Wt, lane);
+  mm_static_pair<Br, ar, 2 * al, 1, ldA, 0, ldT, 0, ldA, 0, CSW1, CSW0>(E, Tb, A, Rnext, Tb + 1024, Wt, lane);
   __syncwarp();
 }
 
@@ -583,11 +586,11 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
         nat_pair_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], Rb1, Rb0, sW + F.w_off[8], As + F.a_off[8], lane);
         if (vec && nxt_img < P.N) prefetch_part(nxt_img, 1);
         nat_pair_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], Rb0, Rb1, sW + F.w_off[7], As + F.a_off[7], lane);
-        nat_pair_step<3, 16>(E, Tb, sW + F.w_off[3], As + F.a_off[3], Rb1, Rb0, sW + F.w_off[6], As + F.a_off[6],
-                             lane);
+        nat_pair_step<3, 16, 16>(E, Tb, sW + F.w_off[3], As + F.a_off[3], Rb1, Rb0, sW + F.w_off[6],
+                                 As + F.a_off[6], lane);
         if (vec && nxt_img < P.N) prefetch_part(nxt_img, 2);
-        // T[(s,a)][B'] (FFMA, K = 16) written swizzled; EL[a'][B'] = sum_(s,a) A4[(s,a)][a'] T[(s,a)][B'] by MMA
-        mm_static<16, 32, 16, 2, 32, 512, 16, 0, 32, 512, 32>(Tb, E, sW + F.w_off[4], lane);
+        // T[(s,a)][B'] = sum_B E4[B][a] W4[s][B][B'], then EL[a'][B'] = sum_(s,a) A4[(s,a)][a'] T[(s,a)][B']
+        mma_static<16, 32, 16, 2, 32, 512, 32, 16, 0, 32, 512>(Tb, E, sW + F.w_off[4], lane);
         __syncwarp();
         mma_static<32, 32, 32, 1, 32, 0, 32, 32, 0, 32, 0>(E, As + F.a_off[4], Tb, lane);
         __syncwarp();
@@ -890,14 +893,17 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   if (!overlap_fast_plan(P, F)) return -1;
   float* small_w = scratch_dev;
   float* wc = scratch_dev + ((F.small_w_total + 31) & ~31);
-  overlap_prep_kernel<float><<<1, 1024, 0, st>>>(reinterpret_cast<const float*>(P.clf), P, F, small_w, wc);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
+  int warps = 8;
   constexpr int PER_WARP = kOvPerWarp;
   const size_t wbytes = (size_t)((F.small_w_total + 31) & ~31) * 4;
   const size_t tabbytes = (((size_t)P.mps_stride * 2 + 15) & ~(size_t)15) + 16;
-  int warps = 8;
   while (warps > 1 && wbytes + tabbytes + (size_t)warps * PER_WARP * 4 > 222 * 1024) --warps;
+  const bool nat = overlap_static_shapes() && overlap_is_natural(P) && F.Spad == 16;
+  const bool mma = nat && overlap_mma() && warps == 8;
+  overlap_prep_kernel<float><<<1, 1024, 0, st>>>(reinterpret_cast<const float*>(P.clf), P, F, small_w, wc,
+                                                 mma ? 4 : -1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
   const size_t smem = wbytes + tabbytes + (size_t)warps * PER_WARP * 4;
   static bool attr_set = false;
   if (!attr_set) {
@@ -911,8 +917,7 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   }
   const int64_t need = (P.N + warps - 1) / warps;
   const int grid = (int)(need < sms ? need : sms);
-  const bool nat = overlap_static_shapes() && overlap_is_natural(P) && F.Spad == 16;
-  if (nat && overlap_mma() && warps == 8)
+  if (mma)
     overlap_fast_kernel<2><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   else if (nat)
     overlap_fast_kernel<1><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
