@@ -274,7 +274,10 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 
 // NS slices of C[m][n] = sum_k Xt[k][m] Y[k][n]; Xt rows of LDX floats and Y rows of LDY floats
 // are swizzled (swz<LDX>, swz<LDY>), C is written with swz<CSW>.  OFFX == 0: Xt shared by the slices.
-template <int M, int N, int K, int NS, int LDC, int OFFC, int CSW, int LDX, int OFFX, int LDY, int OFFY>
+// XROW: the first operand is stored m-major instead, X[m][k] with rows of 16 floats (K = 16, the
+// MPS's own site layout) and its 16-byte quads swizzled, quad q of row m at q ^ ((m >> 1) & 3).
+template <int M, int N, int K, int NS, int LDC, int OFFC, int CSW, int LDX, int OFFX, int LDY, int OFFY,
+          bool XROW = false>
 __device__ __forceinline__ void mma_static(float* __restrict__ C, const float* __restrict__ Xt,
                                            const float* __restrict__ Y, int lane) {
   constexpr int MT = M / 16, NTL = N / 8, KS = K / 8;
@@ -301,10 +304,19 @@ __device__ __forceinline__ void mma_static(float* __restrict__ C, const float* _
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const int m = 16 * mt + g;
-          split_tf32(x0[swz<LDX>(k0, m)], ah[mt][0], al[mt][0]);
-          split_tf32(x0[swz<LDX>(k0, m + 8)], ah[mt][1], al[mt][1]);
-          split_tf32(x1[swz<LDX>(k1, m)], ah[mt][2], al[mt][2]);
-          split_tf32(x1[swz<LDX>(k1, m + 8)], ah[mt][3], al[mt][3]);
+          if constexpr (XROW) {
+            const float* xb = Xt + s * OFFX;
+            const int r0 = (m >> 1) & 3, r1 = ((m + 8) >> 1) & 3;
+            split_tf32(xb[m * 16 + ((((k0 >> 2) ^ r0) << 2) | (k0 & 3))], ah[mt][0], al[mt][0]);
+            split_tf32(xb[(m + 8) * 16 + ((((k0 >> 2) ^ r1) << 2) | (k0 & 3))], ah[mt][1], al[mt][1]);
+            split_tf32(xb[m * 16 + ((((k1 >> 2) ^ r0) << 2) | (k1 & 3))], ah[mt][2], al[mt][2]);
+            split_tf32(xb[(m + 8) * 16 + ((((k1 >> 2) ^ r1) << 2) | (k1 & 3))], ah[mt][3], al[mt][3]);
+          } else {
+            split_tf32(x0[swz<LDX>(k0, m)], ah[mt][0], al[mt][0]);
+            split_tf32(x0[swz<LDX>(k0, m + 8)], ah[mt][1], al[mt][1]);
+            split_tf32(x1[swz<LDX>(k1, m)], ah[mt][2], al[mt][2]);
+            split_tf32(x1[swz<LDX>(k1, m + 8)], ah[mt][3], al[mt][3]);
+          }
         }
       }
       const float* y0 = Y + s * OFFY + k0 * LDY;
@@ -546,7 +558,12 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
 #pragma unroll
       for (int j = 0; j < kOvPre; ++j) {
         const int v = lane + 32 * j;
-        if (NAT && v >= 1 && v <= 340) {
+        if (MMA && v >= 341 && v <= 596) {
+          // site 5 keeps its [s][a][a'] layout (the m-major operand of G), quads swizzled
+          const int i = 4 * v - 1364;
+          const int a = (i >> 4) & 31, q = (i >> 2) & 3;
+          *reinterpret_cast<float4*>(As + 1368 + (i & ~15) + ((q ^ ((a >> 1) & 3)) << 2)) = pre[j];
+        } else if (NAT && v >= 1 && v <= 340) {
           // sites 1..4 of the natural profile keep their layout ([s][a][a'], no row padding):
           // a straight 128-bit copy, 4 floats further on (site 0 is padded from 4 to 8 floats);
           // site 4 (v >= 85) is a fragment operand of the tensor-core path: swizzled rows
@@ -614,7 +631,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       float* G = Tb;                      // [s][a][B']
       float* H = Tb + 1024;               // [s][B][B']
       if constexpr (MMA) {
-        mma_static<32, 16, 16, 2, 16, 512, 16, 32, 512, 16, 0>(G, At, R, lane);
+        mma_static<32, 16, 16, 2, 16, 512, 16, 16, 512, 16, 0, true>(G, At, R, lane);
         __syncwarp();
         mma_static<32, 16, 32, 2, 16, 512, 0, 32, 0, 16, 512>(H, E, G, lane);
       } else {
