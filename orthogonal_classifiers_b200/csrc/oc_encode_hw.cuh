@@ -1057,10 +1057,11 @@ hw_row4q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
         u64 qv[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) qv[e] = shfl2(par ? S[e] : T[e], owner);
-        const float qn2 = dot16<0>(qv, qv);
+        float rT = dot16<0>(qv, T), rS = dot16<0>(qv, S);
+        // |q|^2 is the owner's own dot product (its vector IS q): one shuffle instead of a third dot
+        const float qn2 = __shfl_sync(FULL, par ? rS : rT, owner);
         const bool livej = qn2 > thr2;
         const float inv2 = livej ? 1.f / qn2 : 0.f, invn = livej ? rsqrtf(qn2) : 0.f;
-        float rT = dot16<0>(qv, T), rS = dot16<0>(qv, S);
         if (vT <= j) rT = 0.f;
         if (vS <= j) rS = 0.f;
         const float cT = -rT * inv2, cS = -rS * inv2;
@@ -1366,12 +1367,13 @@ hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
       u64 qv[NE];
 #pragma unroll
       for (int e = 0; e < NE; ++e) qv[e] = shfl2((pc & 1) ? S[e] : T[e], owner);
-      const float qn2 = dot16<1, NE>(qv, qv);
-      // the cached norms only ORDER the pivots; a column whose true residual is below the floor is
+      float rT = dot16<1, NE>(qv, T), rS = dot16<1, NE>(qv, S);
+      // |q|^2 is the owner's own dot product (its column IS q): one shuffle instead of a third dot.
+      // The cached norms only ORDER the pivots; a column whose true residual is below the floor is
       // retired as dead (zero row of R) and the factorisation goes on with the others
+      const float qn2 = __shfl_sync(FULL, (pc & 1) ? rS : rT, owner);
       const bool dead = key == 0u || !(qn2 > thr2);
       const float inv2 = dead ? 0.f : 1.f / qn2, invn = dead ? 0.f : rsqrtf(qn2);
-      float rT = dot16<1, NE>(qv, T), rS = dot16<1, NE>(qv, S);
       const bool isT = 2 * slot == pc, isS = 2 * slot + 1 == pc;
       if (!(nT > 0.f) || isT) rT = 0.f;  // finished columns (norm < 0) and the pivot itself stay
       if (!(nS > 0.f) || isS) rS = 0.f;
