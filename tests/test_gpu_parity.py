@@ -337,6 +337,30 @@ def test_image_families(gpu_lib):
                 assert np.abs(G[np.ix_(nz, nz)] - np.eye(nz.sum())).max() < 20 * TOL["f32"], name
 
 
+def test_full_32x32_images(gpu_lib):
+    """BASELINE.json config 5 uses 32 x 32 = 1024-pixel images: all 16 rows of the 16 x 64
+    unfolding and all 32 of the 32 x 32 one are live (784-pixel images leave 3 / 7 of them
+    zero), which selects the 16-lane step-4 and the full-length step-5 kernels."""
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:32, 0:32]
+    blobs = np.stack([np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * w ** 2)).reshape(-1)
+                      for cx, cy, w in zip(rng.uniform(4, 28, 150), rng.uniform(4, 28, 150), rng.uniform(1, 6, 150))])
+    imgs = np.concatenate([blobs, rng.random((150, 1024))]).astype(np.float32)
+    clf = random_classifier(10, 32, centre=5, seed=12)
+    ref = oracle.overlaps_dense(imgs.astype(np.float64), oracle.dense_classifier(clf))
+    ov, am = gpu_lib.classify(imgs, clf, 32)
+    assert np.abs(ov - ref).max() <= 1e-5 * ref.max()
+    srt = np.sort(ref, axis=1)
+    assert np.all((am == ref.argmax(1)) | ((srt[:, -1] - srt[:, -2]) < 1e-5 * ref.max()))
+    batch = gpu_lib.encode_images(imgs[::25], 32, return_svals=True)
+    sv = batch.svals.cpu().numpy().astype(np.float64)
+    for j, i in enumerate(range(0, len(imgs), 25)):
+        ref_sv = oracle.bond_singular_values(imgs[i].astype(np.float64))
+        for n in range(10):
+            m = min(sv.shape[2], len(ref_sv[n]))
+            assert np.abs(sv[j, n, :m] - ref_sv[n][:m]).max() <= 1e-5 * ref_sv[0][0], (i, n)
+
+
 def test_chunk_boundary_of_the_encoder(gpu_lib):
     """The encoder works in chunks of 131,072 images (workspace and sort lists are
     per chunk): images on both sides of the boundary must come out as they do in
