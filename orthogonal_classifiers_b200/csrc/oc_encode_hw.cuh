@@ -853,9 +853,9 @@ hw_row4p_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
 // directly (normalised columns): no back-substitution, no Gram-Schmidt polish.
 // L by one pass of modified Gram-Schmidt on the rows in registers (R is backward
 // stable even where Q is not orthonormal; Q is not used).  Psi_5 = U^T M_4.
-// Needs k <= 13 (n_pix <= 832).  Same warp lists as hw_row4p_kernel.
+// Same warp lists as hw_row4p_kernel.
 constexpr int kQ4NE = 13;   // packed pairs of an L column: 2k <= 26 elements
-constexpr int kQ4RS = 28;   // floats per row of R in shared memory
+constexpr int kQ4RS = 36;   // floats per row of R in shared memory (2k <= 32 entries + pad)
 // Everything behind the factorisation, for L columns of NE packed pairs (2 gs <= 2 NE elements)
 template <int NE>
 __device__ __forceinline__ void q4_tail(const EncodeParams& P, bool valid, bool ingrp, int gs, int gsz, int gbase,
@@ -1082,7 +1082,8 @@ hw_row4q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
   __syncwarp();
   // vectors of 2 gs elements: the rotation cost is proportional to the padded length
   if (gs <= 10) q4_tail<10>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
-  else q4_tail<kQ4NE>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
+  else if (gs <= kQ4NE) q4_tail<kQ4NE>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);
+  else q4_tail<16>(P, valid, ingrp, gs, gsz, gbase, slot, lane, im, psi_in, psi_out, Rw, thr2);  // n_pix > 832
 }
 
 // counting sort for the packed kernel: bins[0..31] counts, [32..63] first warp of the bin,
@@ -1712,7 +1713,7 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
     const int grid4 = (int)((max_warps + kHwWarps - 1) / kHwWarps);
     const size_t smem4p = (size_t)kHwWarps * 64 * 34 * sizeof(float);
     ee.mark(2, st);
-    if (mgs_step4() && P.n_pix <= 64 * kQ4NE)
+    if (mgs_step4())
       hw_row4q_kernel<<<grid4, kHwWarps * 32, (size_t)kHwWarps * 64 * kQ4RS * sizeof(float), st>>>(P, ws1, ws0, perm,
                                                                                                 bins, keys);
     else
