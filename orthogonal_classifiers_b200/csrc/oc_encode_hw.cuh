@@ -1,30 +1,32 @@
-// Half-warp encoder (fp32, L = 10, 16 < D <= 32): steps 0..5 of the chain.
+// Register-resident encoder kernels (fp32, L = 10, 16 < D <= 32), steps 4..9 of the
+// chain and the older kernels for steps 0..3 (the shipped front end is
+// oc_encode_gram.cuh).  Step-major: one kernel per step over all images, Psi
+// passing through a 4 KB / image global workspace.
 //
-// One image per HALF-warp (two images per warp).  Every step up to the
-// 64 x 16 one has NV <= 32 vectors of 1024/NV*2 ... elements, i.e. exactly
-// 1024 numbers, so each of the 16 lanes always holds 32 elements of the two
-// vectors (T, S) of its slot in registers:
+//   shipped          step  what
+//   hw_row4q_kernel   4    M_4 (2k non-zero rows of 32): Gram-Schmidt on the rows in
+//                          registers -> small factor L (2k x 2k); one-sided Jacobi on
+//                          the columns of L; U = normalised columns, Psi_5 = U^T M_4.
+//                          k lanes per image, floor(32 / k) images of equal k per warp
+//                          (device-side counting sort).
+//   hw_col5q_kernel   5    M_5 (64 x 16): column-pivoted Gram-Schmidt -> R (16 x 16);
+//                          Jacobi on the rows of R, converged vectors = Psi_6;
+//                          U = M_5 V / sigma + Gram-Schmidt polish.  16 lanes per image.
+//   hw_col_kernel<6>, <7>  Jacobi on the columns, 4 / 2 lanes per image
+//   hw_tail89_kernel  8-9  one thread per image
 //
-//   step  mode  vectors x length   slots  lanes/slot
-//    0    row      2 x 512           1      16
-//    1    row      4 x 256           2       8
-//    2    row      8 x 128           4       4
-//    3    row     16 x  64           8       2
-//    4    row     32 x  32          16       1      (rows 26.. are zero for 784 px)
-//    5    col     16 x  64           8       2
+//   behind options (oc_set_option; GPU tests compare them with the shipped ones):
+//   hw_head_kernel, hw_row_kernel<3>   steps 0-2 / 3 by Jacobi on the image unfoldings
+//   hw_row_kernel<4>, hw_row4p_kernel  step 4 by Jacobi on the rows of M_4 (16 lanes per
+//                          image / packed), U = M W^T S^-2 + polish
+//   hw_col_kernel<5>       step 5 by Jacobi on the 64-element columns
 //
-// Compared with the one-image-per-warp kernels (oc_encode_fast.cuh) the
-// rotation-parameter chain and the shuffle reductions are shared by twice as
-// many elements, and
-//   * step 4 rotates ROWS (only 2*rank(bond 4) <= 26 of the 32 are non-zero,
-//     ~20 for MNIST-like images, so the odd-even line is that short), and
-//   * no step accumulates U: the converged rows ARE W = S.V^T (next Psi), and
-//     A_n = U = M W^T S^-2 is one small product at the end of the step.  An
-//     error in column k of U grows like sigma_max/sigma_k but enters every
-//     gauge-invariant quantity weighted by sigma_k, so amplitudes, singular
-//     values and overlaps keep fp32 accuracy (tests/test_gpu_parity.py).
-// Steps run as separate kernels (head = 0..2 | 3 | 4 | 5), Psi passing through
-// the global workspace like the v3 chain; steps 6..9 reuse the v3 tail kernel.
+// Common machinery: every lane holds the two vectors (T, S) of its slot in
+// registers as packed pairs (fma.rn.f32x2); odd-even ordering (round A rotates
+// (T_k, S_k), round B (S_k, T_{k+1}) after moving T one slot down and back; every
+// rotation swaps positions); cached squared norms, refreshed each sweep;
+// branch-free rotation parameters; a `hold` coefficient set makes a lane's
+// rotation an exact no-op, so results never depend on the images sharing a warp.
 #pragma once
 #include "oc_encode_fast.cuh"
 

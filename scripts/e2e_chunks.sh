@@ -1,6 +1,6 @@
 #!/bin/bash
 # end-to-end throughput for several H2D/compute pipeline chunk sizes
-for c in 8750 17500 23334 35000 70000; do
+for c in ${CHUNKS:-8750 17500 23334 35000 70000}; do
   python bench.py --no-cpu-baseline --e2e-chunk $c 2>/dev/null | tail -1 > /tmp/b.json
   python - "$c" <<'P'
 import json, sys
