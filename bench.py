@@ -31,9 +31,9 @@ FLOP_STEP4 = 721_920         # the 32 x 32 SVD step (bond 4 ->
 FLOP_CLASSIFY = 257_456
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel
 # (hw_row4q_kernel, 70,000 images) from `ncu --set full` of this command
-# (profiles/ncu_step4_r1.csv: 204.57 MB read + 522.79 MB written; algorithmic
+# (profiles/ncu_step4_r1.csv: 205.31 MB read + 526.08 MB written; algorithmic
 # <= 3 x 4 KB per image = 860 MB: Psi_4 live rows in, Psi_5 and A_4 out)
-TRAFFIC_STEP4_BYTES = 727_363_584
+TRAFFIC_STEP4_BYTES = 731_385_600
 BYTES_IMG = 784 * 4 + 16 * 4 + 4
 
 
