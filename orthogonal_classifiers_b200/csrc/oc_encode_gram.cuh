@@ -1,6 +1,7 @@
 // Gram-matrix front end of the half-warp encoder: steps 0..3 of the chain for
-// L = 10, D > 16 (no truncation before bond 5), replacing the head (steps 0-2)
-// and step-3 Jacobi kernels of oc_encode_hw.cuh.
+// L = 10, D >= 8 (no truncation before bond 4; for 8 <= D < 16 step 3 keeps the D
+// largest singular vectors), replacing the head (steps 0-2) and step-3 Jacobi
+// kernels of oc_encode_hw.cuh.
 //
 // With X_n the (2^(n+1) x 2^(9-n)) row unfolding of the padded image
 // (tools.py:218-220), step n of the chain is the SVD of
@@ -581,7 +582,8 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
         A[l * 8] = fmaf(up[0], c0, fmaf(up[1], c1, fmaf(up[2], c2, up[3] * c3)));
       }
     }
-    {  // n = 3: lane = r, all (s, l)
+    {  // n = 3: lane = r, all (s, l); bond 4 = min(16, D) columns (8 <= D < 16 truncates here)
+      const int r4b = P.bonds[4];
       const float* un = Uf + g_off(3) + l16 * 17;
       float col[16];
 #pragma unroll
@@ -597,8 +599,10 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
           a0 = fmaf(u, col[2 * i], a0);
           a1 = fmaf(u, col[2 * i + 1], a1);
         }
-        A[l * 16] = a0;
-        A[(8 + l) * 16] = a1;
+        if (l16 < r4b) {
+          A[l * r4b] = a0;
+          A[(8 + l) * r4b] = a1;
+        }
       }
     }
   }

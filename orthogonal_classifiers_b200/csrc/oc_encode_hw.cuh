@@ -1650,7 +1650,9 @@ __global__ void __launch_bounds__(128) hw_tail89_kernel(const __grid_constant__ 
   }
 }
 
-inline bool supported(const EncodeParams& P) { return P.L == 10 && P.D > 16; }
+// D >= 8: bonds 1..3 are the natural 2, 4, 8, so steps 0..2 never truncate (the Gram front end
+// needs that); smaller D runs the one-image-per-warp kernels of oc_encode_fast.cuh
+inline bool supported(const EncodeParams& P) { return P.L == 10 && P.D >= 8; }
 
 }  // namespace hw
 namespace gram {  // oc_encode_gram.cuh: steps 0..3 from the 16 x 16 Gram matrix
