@@ -63,6 +63,9 @@ const char* oc_last_error(void);
  *   "enc_qr5"  = 0  step 5 without the pivoted Gram-Schmidt preconditioning
  *   "enc_sort" = 0  no device-side sort of the images by live rows
  *   "ov_static" = 0 run-time shapes in the overlap kernel for the 32/32 profile
+ *   "ov_mma"   = 0  FFMA instead of tensor-core contractions in the overlap kernel
+ *   "ov_pad"   = 0  D_encode < 32 images through the run-time-shaped overlap kernel
+ *                   instead of zero-padded through the 32/32 one
  *   "enc_events"    see oc_encode_step_ms
  * Unknown keys return OC_E_ARG. */
 int oc_set_option(const char* key, int value);

@@ -107,6 +107,10 @@ int oc_set_option(const char* key, int value) {
     oc::hw::sort_pairs() = value;
     return OC_OK;
   }
+  if (key && !strcmp(key, "ov_pad")) {
+    oc::overlap_pad() = value;
+    return OC_OK;
+  }
   if (key && !strcmp(key, "ov_mma")) {
     oc::overlap_mma() = value;
     return OC_OK;

@@ -450,14 +450,28 @@ inline bool overlap_is_natural(const OverlapParams& P) {
   }
   return true;
 }
+// natural-32 classifier, image bonds anywhere below the natural profile (D_encode < 32)
+inline bool overlap_is_padded_natural(const OverlapParams& P) {
+  if (P.L != 10 || P.c != 5 || P.S != 16) return false;
+  bool smaller = false;
+  for (int n = 0; n <= 10; ++n) {
+    const int b = n <= 5 ? (1 << n) : (1 << (10 - n));
+    if (P.B[n] != b || P.a[n] > b || P.a[n] < 1) return false;
+    smaller = smaller || P.a[n] < b;
+  }
+  return smaller;
+}
 
 // MODE 0: run-time shapes; 1: natural 32/32 profile, compile-time shapes, FFMA; 2: the same with
-// the three largest contractions on the tensor cores (3xTF32)
+// the GEMM-shaped contractions on the tensor cores (3xTF32); 3: as 2 for image MPSs of any smaller
+// bond dimension (D_encode < 32) against the natural-32 classifier: the sites are staged
+// zero-padded to the natural profile (the padding is written once per warp), so a truncated
+// encoding costs what the full one does instead of the run-time-shaped kernel's 2.5x
 template <int MODE>
 __global__ void __launch_bounds__(256, 1)
 overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_constant__ OverlapFast F,
                     const float* __restrict__ small_w, const float* __restrict__ wc) {
-  constexpr bool NAT = MODE > 0, MMA = MODE == 2;
+  constexpr bool NAT = MODE > 0, MMA = MODE >= 2, PAD = MODE == 3;
   extern __shared__ __align__(128) unsigned char smem_ov[];
   float* sW = reinterpret_cast<float*>(smem_ov);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -514,7 +528,16 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
     const int al = P.a[n], ar = P.a[n + 1];
     const int q = i / ar, ap = i - q * ar;  // q = s*al + a
     int d;
-    if (n < c) {
+    if constexpr (PAD) {
+      // destination in the NATURAL profile's layout (F.a_off is the natural one), with the
+      // fragment swizzles of sites 4 and 5
+      const int AL = n <= 5 ? 1 << n : 1 << (10 - n), AR = n < 5 ? 2 << n : 1 << (9 - n);
+      const int sdx = q / al, a = q - sdx * al;
+      if (n < 4) d = (sdx * AL + a) * r4(AR) + ap;
+      else if (n == 4) d = (sdx * 16 + a) * 32 + swz<32>(sdx * 16 + a, ap);
+      else if (n == 5) d = sdx * 512 + a * 16 + ((((ap >> 2) ^ ((a >> 1) & 3)) << 2) | (ap & 3));
+      else d = (sdx * AR + ap) * r4(AL) + a;
+    } else if (n < c) {
       d = q * r4(ar) + ap;
     } else {
       const int sdx = q / al, a = q - sdx * al;
@@ -546,6 +569,10 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       if ((j * 4) / kOvPre == part && 4 * v < stride) pre[j] = __ldcs(src + v);
     }
   };
+  if constexpr (PAD) {
+    for (int i = lane; i < kOvMaxA; i += 32) As[i] = 0.f;  // the padding stays zero: the scatter never touches it
+    __syncwarp();
+  }
   if (vec && (int64_t)blockIdx.x * nwarps + warp < P.N) prefetch((int64_t)blockIdx.x * nwarps + warp);
   // the trip count is per CTA (the tensor-core label sums below are CTA-wide); a warp whose image
   // index runs past N only takes part in the barriers
@@ -558,12 +585,12 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
 #pragma unroll
       for (int j = 0; j < kOvPre; ++j) {
         const int v = lane + 32 * j;
-        if (MMA && v >= 341 && v <= 596) {
+        if (MMA && !PAD && v >= 341 && v <= 596) {
           // site 5 keeps its [s][a][a'] layout (the m-major operand of G), quads swizzled
           const int i = 4 * v - 1364;
           const int a = (i >> 4) & 31, q = (i >> 2) & 3;
           *reinterpret_cast<float4*>(As + 1368 + (i & ~15) + ((q ^ ((a >> 1) & 3)) << 2)) = pre[j];
-        } else if (NAT && v >= 1 && v <= 340) {
+        } else if (NAT && !PAD && v >= 1 && v <= 340) {
           // sites 1..4 of the natural profile keep their layout ([s][a][a'], no row padding):
           // a straight 128-bit copy, 4 floats further on (site 0 is padded from 4 to 8 floats);
           // site 4 (v >= 85) is a fragment operand of the tensor-core path: swizzled rows
@@ -860,6 +887,10 @@ inline int& overlap_mma() {
   static int v = 1;
   return v;
 }
+inline int& overlap_pad() {
+  static int v = 1;
+  return v;
+}
 
 // Host-side plan; returns false when the shapes do not fit the fast kernel.
 inline bool overlap_fast_plan(const OverlapParams& P, OverlapFast& F) {
@@ -916,7 +947,17 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   const size_t tabbytes = (((size_t)P.mps_stride * 2 + 15) & ~(size_t)15) + 16;
   while (warps > 1 && wbytes + tabbytes + (size_t)warps * PER_WARP * 4 > 222 * 1024) --warps;
   const bool nat = overlap_static_shapes() && overlap_is_natural(P) && F.Spad == 16;
-  const bool mma = nat && overlap_mma() && warps == 8;
+  // D_encode < 32 against the natural-32 classifier: the image sites are staged zero-padded to the
+  // natural profile, so the shared-memory offsets are those of the natural plan
+  const bool pad = overlap_static_shapes() && overlap_mma() && overlap_pad() && warps == 8 && F.Spad == 16 &&
+                   overlap_is_padded_natural(P);
+  if (pad) {
+    OverlapParams Pn = P;
+    for (int n = 0; n <= 10; ++n) Pn.a[n] = n <= 5 ? (1 << n) : (1 << (10 - n));
+    Pn.amax = 32;
+    if (!overlap_fast_plan(Pn, F)) return -1;
+  }
+  const bool mma = (nat || pad) && overlap_mma() && warps == 8;
   overlap_prep_kernel<float><<<1, 1024, 0, st>>>(reinterpret_cast<const float*>(P.clf), P, F, small_w, wc,
                                                  mma ? 4 : -1);
   cudaError_t e = cudaGetLastError();
@@ -930,11 +971,15 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(overlap_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(overlap_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t need = (P.N + warps - 1) / warps;
   const int grid = (int)(need < sms ? need : sms);
-  if (mma)
+  if (mma && pad)
+    overlap_fast_kernel<3><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+  else if (mma)
     overlap_fast_kernel<2><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   else if (nat)
     overlap_fast_kernel<1><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);

@@ -225,7 +225,7 @@ def test_generic_and_specialised_kernels_agree(gpu_lib):
             assert np.abs(ov_fast - ov_gen).max() <= 1e-5 * ov_gen.max()
 
 
-@pytest.mark.parametrize("option", ["enc_gram", "enc_pack", "enc_mgs4", "enc_qr5", "ov_static", "ov_mma"])
+@pytest.mark.parametrize("option", ["enc_gram", "enc_pack", "enc_mgs4", "enc_qr5", "ov_static", "ov_mma", "ov_pad"])
 def test_alternative_code_paths_agree(gpu_lib, option):
     """Every fast path has its predecessor behind an option: the Gram-matrix front
     end (steps 0-3) vs. the Jacobi head kernels, the packed step 4 vs. the paired
@@ -235,12 +235,13 @@ def test_alternative_code_paths_agree(gpu_lib, option):
     imgs = np.concatenate([synthetic_images(300, seed=21), adversarial_images()]).astype(np.float32)
     clf = random_classifier(10, 32, centre=5, seed=4)
     for D in (32, 20):
+        both = D == 32 or option == "ov_pad"   # (truncated encodings: only the overlap options compare overlaps)
         new = gpu_lib.encode_images(imgs, D, return_svals=True)
-        ov_new = gpu_lib.label_overlaps(new, clf) if D == 32 else None
+        ov_new = gpu_lib.label_overlaps(new, clf) if both else None
         batched.set_option(option, 0)
         try:
             old = gpu_lib.encode_images(imgs, D, return_svals=True)
-            ov_old = gpu_lib.label_overlaps(old, clf) if D == 32 else None
+            ov_old = gpu_lib.label_overlaps(old, clf) if both else None
         finally:
             batched.set_option(option, 1)
         sn, so = new.svals.cpu().numpy(), old.svals.cpu().numpy()
@@ -249,7 +250,7 @@ def test_alternative_code_paths_agree(gpu_lib, option):
             a = oracle.mps_to_state([x.astype(np.float64) for x in new.sites_numpy(i)])
             b = oracle.mps_to_state([x.astype(np.float64) for x in old.sites_numpy(i)])
             assert _state_err(a, b) < 1e-5
-        if D == 32:
+        if both:
             assert np.abs(ov_new - ov_old).max() <= 1e-5 * ov_old.max()
 
 
