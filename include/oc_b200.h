@@ -55,7 +55,7 @@ const char* oc_last_error(void);
 
 /* Test/diagnostic switches (every alternative is CUDA; there is no CPU path).
  *   "force_generic" = 1  every call through the runtime-shaped kernels
- *   "enc_hw"   = 0  D > 16 encodes with the one-image-per-warp kernels
+ *   "enc_hw"   = 0  D >= 8 encodes with the one-image-per-warp kernels
  *   "enc_gram" = 0  steps 0-3 by Jacobi on the image unfoldings instead of the
  *                   16 x 16 Gram matrix
  *   "enc_pack" = 0  step 4 with 16 lanes per image instead of packed warps

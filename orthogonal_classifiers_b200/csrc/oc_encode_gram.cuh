@@ -558,7 +558,7 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
     if (valid && j < rows_live) xa[j] = pix4m<MODE>(src, 64 * j + 4 * l16);
   }
 
-  // ---- A_n[(s,l), r] = sum_i U^(n-1)[i][l] U^(n)[2i+s][r]  (D > 16: natural bonds 2^n) ----
+  // ---- A_n[(s,l), r] = sum_i U^(n-1)[i][l] U^(n)[2i+s][r]  (D >= 8: bonds 1..3 are the natural 2, 4, 8) ----
   if (valid) {
     float* mps = reinterpret_cast<float*>(P.mps_out) + (size_t)im * P.mps_stride;
     if (l16 < 4) {  // n = 0: A_0[(s,0), r] = U^(0)[s][r]

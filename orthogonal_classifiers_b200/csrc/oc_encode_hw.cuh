@@ -1,4 +1,4 @@
-// Register-resident encoder kernels (fp32, L = 10, 16 < D <= 32), steps 4..9 of the
+// Register-resident encoder kernels (fp32, L = 10, 8 <= D <= 32), steps 4..9 of the
 // chain and the older kernels for steps 0..3 (the shipped front end is
 // oc_encode_gram.cuh).  Step-major: one kernel per step over all images, Psi
 // passing through a 4 KB / image global workspace.
