@@ -166,6 +166,11 @@ __device__ __forceinline__ void mm_slices(float* __restrict__ C, int ldc, int of
                                           int M, int N, int K, int nslice, int lane) {
   if (M * N * nslice == 1024 && (M & 7) == 0 && (N & 3) == 0) {
     mm_kmajor_84(C, ldc, offC, Xt, ldx, offX, Y, ldy, offY, M, N, K, lane);
+  } else if (M * N == 1024 && (M & 7) == 0 && (N & 3) == 0) {
+    // 1,024 outputs per slice (last-site-hairy classifiers: 32 x 32 environments): one 8 x 4 tile
+    // per lane and slice
+    for (int s = 0; s < nslice; ++s)
+      mm_kmajor_84(C + s * offC, ldc, 0, Xt + s * offX, ldx, 0, Y + s * offY, ldy, 0, M, N, K, lane);
   } else {
     for (int s = 0; s < nslice; ++s)
       mm_kmajor(C + s * offC, ldc, Xt + s * offX, ldx, Y + s * offY, ldy, M, N, K, lane);

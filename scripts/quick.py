@@ -10,7 +10,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 70000
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 imgs = synthetic_images(8192, seed=2, labels=np.arange(8192) % 10, dtype=np.float32)
 imgs = torch.from_numpy(np.tile(imgs, ((N + 8191) // 8192, 1))[:N]).cuda()
-clf = oc.DeviceClassifier(random_classifier(10, 32, centre=5, seed=1))
+clf = oc.DeviceClassifier(random_classifier(10, 32, centre=int(sys.argv[3]) if len(sys.argv) > 3 else 5, seed=1))
 
 def timeit(fn, reps=10):
     for _ in range(3): fn()
