@@ -222,34 +222,40 @@ template <int M, int N, int K, int NS, int LDC, int OFFC, int LDX, int OFFX, int
 __device__ __forceinline__ void mm_static(float* __restrict__ C, const float* __restrict__ Xt,
                                           const float* __restrict__ Y, int lane) {
   constexpr int OUT = M * N * NS;
+  // outputs per lane ~ OUT / 32: 8x4 (>= 1024; 2,048 outputs take two passes), 4x4, 4x2, 2x2, 2x1, 1x1
   constexpr int TM = OUT >= 1024 ? 8 : (OUT >= 256 ? 4 : (OUT >= 64 ? 2 : 1));
-  constexpr int TN = OUT >= 1024 ? 4 : (OUT >= 256 ? 2 : 1);
+  constexpr int TN = OUT >= 512 ? 4 : (OUT >= 128 ? 2 : 1);
   static_assert(M % TM == 0 && N % TN == 0, "tile does not divide the shape");
   constexpr int tm = M / TM, tn = N / TN, per = tm * tn, NT = per * NS;
-  static_assert(NT <= 32, "more tiles than lanes");
-  if (NT < 32 && lane >= NT) return;
-  const int s = lane / per, t = lane % per;
-  const int tj = t / tm, ti = t % tm;
-  const float* xp = Xt + s * OFFX + TM * ti;
-  const float* yp = Y + s * OFFY + TN * tj;
-  float acc[TM][TN];
+  static_assert(NT <= 64, "more than two passes of tiles");
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
+  for (int t0 = 0; t0 < NT; t0 += 32) {
+    const int tile = t0 + lane;
+    if (tile < NT) {
+      const int s = tile / per, t = tile % per;
+      const int tj = t / tm, ti = t % tm;
+      const float* xp = Xt + s * OFFX + TM * ti;
+      const float* yp = Y + s * OFFY + TN * tj;
+      float acc[TM][TN];
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 #pragma unroll(K <= 8 ? K : 8)
-  for (int k = 0; k < K; ++k) {
-    float xv[TM], yv[TN];
-    ldv<TM>(xv, xp + k * LDX);
-    ldv<TN>(yv, yp + k * LDY);
+      for (int k = 0; k < K; ++k) {
+        float xv[TM], yv[TN];
+        ldv<TM>(xv, xp + k * LDX);
+        ldv<TN>(yv, yp + k * LDY);
 #pragma unroll
-    for (int i = 0; i < TM; ++i)
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+      }
+      float* cp = C + s * OFFC + (TM * ti) * LDC;
+#pragma unroll
+      for (int i = 0; i < TM; ++i) stv<TN>(cp + i * LDC + swz<CSW>(TM * ti + i, TN * tj), acc[i]);
+    }
   }
-  float* cp = C + s * OFFC + (TM * ti) * LDC;
-#pragma unroll
-  for (int i = 0; i < TM; ++i) stv<TN>(cp + i * LDC + swz<CSW>(TM * ti + i, TN * tj), acc[i]);
 }
 
 // ---- tensor-core contractions (mma.sync m16n8k8, TF32 inputs, fp32 accumulate) ----
@@ -447,6 +453,37 @@ __device__ __forceinline__ void nat_right_step(float* R, float* R2, float* Tb, c
   __syncwarp();
 }
 
+// left step n (0..8) of the LAST-site-hairy natural-32 profile: image bonds natural, classifier
+// bonds [1,2,4,8,16,32,32,32,32,32,1] (fMPO.compress_one_site, fMPO.py:240-336)
+template <int NSITE>
+__device__ __forceinline__ void last_left_step(float* E, float* Tb, const float* W, const float* A, int lane) {
+  constexpr int al = NSITE <= 5 ? 1 << NSITE : 1 << (10 - NSITE);
+  constexpr int ar = NSITE < 5 ? 2 << NSITE : 1 << (9 - NSITE);
+  constexpr int Bl = NSITE <= 5 ? 1 << NSITE : 32, Br = NSITE < 5 ? 2 << NSITE : 32;
+  constexpr int ldE = (al + 3) & ~3, ldW = (Br + 3) & ~3, ldA = (ar + 3) & ~3, ldT = ldW;
+  // T[(s,a)][B'] = sum_B Et[B][a] W[s][B][B']
+  mm_static<al, Br, Bl, 2, ldT, al * ldT, ldE, 0, ldW, Bl * ldW>(Tb, E, W, lane);
+  __syncwarp();
+  if constexpr (NSITE + 1 < 9) {
+    // Et'[B'][a'] = sum_(s,a) T[(s,a)][B'] A[(s,a)][a']
+    mm_static<Br, ar, 2 * al, 1, ldA, 0, ldT, 0, ldA, 0>(E, Tb, A, lane);
+  } else {
+    // EL[a'][B'] = sum_(s,a) A[(s,a)][a'] T[(s,a)][B']
+    mm_static<ar, Br, 2 * al, 1, ldT, 0, ldA, 0, ldT, 0>(E, A, Tb, lane);
+  }
+  __syncwarp();
+}
+
+inline bool overlap_is_last_natural(const OverlapParams& P) {
+  if (P.L != 10 || P.c != 9 || P.S != 16) return false;
+  for (int n = 0; n <= 10; ++n) {
+    const int a = n <= 5 ? (1 << n) : (1 << (10 - n));
+    const int b = n == 10 ? 1 : (n <= 5 ? (1 << n) : 32);
+    if (P.B[n] != b || P.a[n] > a || P.a[n] < 1) return false;
+  }
+  return true;
+}
+
 inline bool overlap_is_natural(const OverlapParams& P) {
   if (P.L != 10 || P.c != 5 || P.S != 16) return false;
   for (int n = 0; n <= 10; ++n) {
@@ -471,12 +508,14 @@ inline bool overlap_is_padded_natural(const OverlapParams& P) {
 // the GEMM-shaped contractions on the tensor cores (3xTF32); 3: as 2 for image MPSs of any smaller
 // bond dimension (D_encode < 32) against the natural-32 classifier: the sites are staged
 // zero-padded to the natural profile (the padding is written once per warp), so a truncated
-// encoding costs what the full one does instead of the run-time-shaped kernel's 2.5x
+// encoding costs what the full one does instead of the run-time-shaped kernel's 2.5x;
+// 4: last-site-hairy natural-32 classifier (c = 9), compile-time shapes, FFMA, images of any
+// D_encode <= 32 staged zero-padded
 template <int MODE>
 __global__ void __launch_bounds__(256, 1)
 overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_constant__ OverlapFast F,
                     const float* __restrict__ small_w, const float* __restrict__ wc) {
-  constexpr bool NAT = MODE > 0, MMA = MODE >= 2, PAD = MODE == 3;
+  constexpr bool NAT = MODE >= 1 && MODE <= 3, MMA = MODE == 2 || MODE == 3, PAD = MODE == 3, LAST = MODE == 4;
   extern __shared__ __align__(128) unsigned char smem_ov[];
   float* sW = reinterpret_cast<float*>(smem_ov);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -533,7 +572,13 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
     const int al = P.a[n], ar = P.a[n + 1];
     const int q = i / ar, ap = i - q * ar;  // q = s*al + a
     int d;
-    if constexpr (PAD) {
+    if constexpr (LAST) {
+      // natural-profile destination; every site but the last keeps [s][a][a'] (ld r4(a')), the
+      // hairy site 9 is [s][a'][a]
+      const int AL = n <= 5 ? 1 << n : 1 << (10 - n), AR = n < 5 ? 2 << n : 1 << (9 - n);
+      const int sdx = q / al, a = q - sdx * al;
+      d = n < 9 ? (sdx * AL + a) * r4(AR) + ap : (sdx * AR + ap) * r4(AL) + a;
+    } else if constexpr (PAD) {
       // destination in the NATURAL profile's layout (F.a_off is the natural one), with the
       // fragment swizzles of sites 4 and 5
       const int AL = n <= 5 ? 1 << n : 1 << (10 - n), AR = n < 5 ? 2 << n : 1 << (9 - n);
@@ -574,7 +619,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       if ((j * 4) / kOvPre == part && 4 * v < stride) pre[j] = __ldcs(src + v);
     }
   };
-  if constexpr (PAD) {
+  if constexpr (PAD || LAST) {
     for (int i = lane; i < kOvMaxA; i += 32) As[i] = 0.f;  // the padding stays zero: the scatter never touches it
     __syncwarp();
   }
@@ -623,7 +668,61 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
     }
     __syncwarp();
 
-    if constexpr (NAT) {
+    if constexpr (LAST) {
+      // ---- last-site-hairy natural-32 profile: nine left steps with constant shapes ----
+      float* E = Eb;
+      if (lane == 0) E[0] = 1.f;
+      __syncwarp();
+      last_left_step<0>(E, Tb, sW + F.w_off[0], As + F.a_off[0], lane);
+      last_left_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], lane);
+      last_left_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], lane);
+      last_left_step<3>(E, Tb, sW + F.w_off[3], As + F.a_off[3], lane);
+      last_left_step<4>(E, Tb, sW + F.w_off[4], As + F.a_off[4], lane);
+      last_left_step<5>(E, Tb, sW + F.w_off[5], As + F.a_off[5], lane);
+      last_left_step<6>(E, Tb, sW + F.w_off[6], As + F.a_off[6], lane);
+      last_left_step<7>(E, Tb, sW + F.w_off[7], As + F.a_off[7], lane);
+      last_left_step<8>(E, Tb, sW + F.w_off[8], As + F.a_off[8], lane);
+      // hairy site 9: a = 2, a' = 1, B = 32, B' = 1: H[s][B] = sum_a EL[a][B] A9[s][a];
+      // out[l] = sum_(s,B) Wc[(s,B)][l] H[s][B]   (Wc rows of r4(1) * 16 floats); lane = B
+      const float* A9 = As + F.a_off[9];  // [s][a' = 0][a], ld 4
+      float acc[16];
+#pragma unroll
+      for (int l = 0; l < 16; ++l) acc[l] = 0.f;
+#pragma unroll
+      for (int sdx = 0; sdx < 2; ++sdx) {
+        const float h = fmaf(E[lane], A9[sdx * 4], E[32 + lane] * A9[sdx * 4 + 1]);
+        const float4* wr = reinterpret_cast<const float4*>(wc + (size_t)(sdx * 32 + lane) * 64);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 w4 = __ldg(wr + q4);
+          acc[4 * q4] = fmaf(w4.x, h, acc[4 * q4]);
+          acc[4 * q4 + 1] = fmaf(w4.y, h, acc[4 * q4 + 1]);
+          acc[4 * q4 + 2] = fmaf(w4.z, h, acc[4 * q4 + 2]);
+          acc[4 * q4 + 3] = fmaf(w4.w, h, acc[4 * q4 + 3]);
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int l = 0; l < 16; ++l) acc[l] += __shfl_xor_sync(FULL, acc[l], o);
+      }
+      float v = 0.f;
+#pragma unroll
+      for (int l = 0; l < 16; ++l) v = lane == l ? acc[l] : v;
+      v = fabsf(v);
+      if (lane < 16) reinterpret_cast<float*>(P.overlaps)[(size_t)img * 16 + lane] = v;
+      if (P.argmax) {
+        float best = lane < 16 ? v : -1.f;
+        int besti = lane;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          const float ob = __shfl_xor_sync(FULL, best, o);
+          const int oi = __shfl_xor_sync(FULL, besti, o);
+          if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) P.argmax[img] = besti;
+      }
+    } else if constexpr (NAT) {
       // ---- natural 32 / 32 profile: every shape a constant ----
       float* E = Eb;
       if (lane == 0) { E[0] = 1.f; Rb0[0] = 1.f; }
@@ -956,7 +1055,8 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   // natural profile, so the shared-memory offsets are those of the natural plan
   const bool pad = overlap_static_shapes() && overlap_mma() && overlap_pad() && warps == 8 && F.Spad == 16 &&
                    overlap_is_padded_natural(P);
-  if (pad) {
+  const bool last = overlap_static_shapes() && overlap_pad() && F.Spad == 16 && overlap_is_last_natural(P);
+  if (pad || last) {
     OverlapParams Pn = P;
     for (int n = 0; n <= 10; ++n) Pn.a[n] = n <= 5 ? (1 << n) : (1 << (10 - n));
     Pn.amax = 32;
@@ -978,11 +1078,15 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(overlap_fast_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(overlap_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t need = (P.N + warps - 1) / warps;
   const int grid = (int)(need < sms ? need : sms);
-  if (mma && pad)
+  if (last)
+    overlap_fast_kernel<4><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+  else if (mma && pad)
     overlap_fast_kernel<3><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   else if (mma)
     overlap_fast_kernel<2><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
