@@ -42,7 +42,7 @@ struct OverlapFast {
 // ---- classifier re-layout (one small launch per overlap call) --------------
 template <typename TIN>
 __global__ void overlap_prep_kernel(const TIN* __restrict__ clf, OverlapParams P, OverlapFast F,
-                                    float* __restrict__ small_w, float* __restrict__ wc, int swz_site = -1) {
+                                    float* __restrict__ small_w, float* __restrict__ wc, unsigned swz_mask = 0u) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int i = tid; i < F.small_w_total; i += nth) small_w[i] = 0.f;
   for (int64_t i = tid; i < F.wc_elems; i += nth) wc[i] = 0.f;
@@ -62,8 +62,8 @@ __global__ void overlap_prep_kernel(const TIN* __restrict__ clf, OverlapParams P
       const int ld = r4(Br);
       for (int i = tid; i < 2 * Bl * Br; i += nth) {
         const int bp = i % Br, sb = i / Br;  // sb = s*Bl + b
-        // swz_site: this site is a tensor-core fragment operand (rows of 32): bank swizzle, see swz<32>
-        const int col = n == swz_site ? (bp ^ ((sb & 3) << 3)) : bp;
+        // swz_mask bit n: this site is a tensor-core fragment operand (rows of 32): bank swizzle, see swz<32>
+        const int col = ((swz_mask >> n) & 1u) ? (bp ^ ((sb & 3) << 3)) : bp;
         small_w[F.w_off[n] + (int64_t)sb * ld + col] = (float)W[i];
       }
     } else {
@@ -510,12 +510,14 @@ inline bool overlap_is_padded_natural(const OverlapParams& P) {
 // zero-padded to the natural profile (the padding is written once per warp), so a truncated
 // encoding costs what the full one does instead of the run-time-shaped kernel's 2.5x;
 // 4: last-site-hairy natural-32 classifier (c = 9), compile-time shapes, FFMA, images of any
-// D_encode <= 32 staged zero-padded
+// D_encode <= 32 staged zero-padded; 5: the same with the contractions of sites 4-6 (70 % of the
+// MACs) on the tensor cores
 template <int MODE>
 __global__ void __launch_bounds__(256, 1)
 overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_constant__ OverlapFast F,
                     const float* __restrict__ small_w, const float* __restrict__ wc) {
-  constexpr bool NAT = MODE >= 1 && MODE <= 3, MMA = MODE == 2 || MODE == 3, PAD = MODE == 3, LAST = MODE == 4;
+  constexpr bool NAT = MODE >= 1 && MODE <= 3, MMA = MODE == 2 || MODE == 3, PAD = MODE == 3;
+  constexpr bool LAST = MODE == 4 || MODE == 5, LMMA = MODE == 5;
   extern __shared__ __align__(128) unsigned char smem_ov[];
   float* sW = reinterpret_cast<float*>(smem_ov);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -578,6 +580,8 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       const int AL = n <= 5 ? 1 << n : 1 << (10 - n), AR = n < 5 ? 2 << n : 1 << (9 - n);
       const int sdx = q / al, a = q - sdx * al;
       d = n < 9 ? (sdx * AL + a) * r4(AR) + ap : (sdx * AR + ap) * r4(AL) + a;
+      if (LMMA && n == 4) d = (sdx * 16 + a) * 32 + swz<32>(sdx * 16 + a, ap);   // fragment operands
+      if (LMMA && n == 5) d = (sdx * 32 + a) * 16 + swz<16>(sdx * 32 + a, ap);
     } else if constexpr (PAD) {
       // destination in the NATURAL profile's layout (F.a_off is the natural one), with the
       // fragment swizzles of sites 4 and 5
@@ -677,9 +681,27 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       last_left_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], lane);
       last_left_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], lane);
       last_left_step<3>(E, Tb, sW + F.w_off[3], As + F.a_off[3], lane);
-      last_left_step<4>(E, Tb, sW + F.w_off[4], As + F.a_off[4], lane);
-      last_left_step<5>(E, Tb, sW + F.w_off[5], As + F.a_off[5], lane);
-      last_left_step<6>(E, Tb, sW + F.w_off[6], As + F.a_off[6], lane);
+      if constexpr (LMMA) {
+        // site 4: T (FFMA, K = 16) written swizzled; Et'[B'][a'] = sum_(s,a) T[(s,a)][B'] A4[(s,a)][a']
+        mm_static<16, 32, 16, 2, 32, 512, 16, 0, 32, 512, 32>(Tb, E, sW + F.w_off[4], lane);
+        __syncwarp();
+        mma_static<32, 32, 32, 1, 32, 0, 32, 32, 0, 32, 0>(E, Tb, As + F.a_off[4], lane);
+        __syncwarp();
+        // site 5: T[(s,a)][B'] = sum_B Et[B][a] W5[s][B][B'] (2 x 32x32x32), then Et' (32 x 16, K = 64)
+        mma_static<32, 32, 32, 2, 32, 1024, 32, 32, 0, 32, 1024>(Tb, E, sW + F.w_off[5], lane);
+        __syncwarp();
+        mma_static<32, 16, 64, 1, 16, 0, 16, 32, 0, 16, 0>(E, Tb, As + F.a_off[5], lane);
+        __syncwarp();
+        // site 6: T (2 x 16x32x32), then Et' (32 x 8, K = 32; rows of 8 floats need no swizzle)
+        mma_static<16, 32, 32, 2, 32, 512, 32, 16, 0, 32, 1024>(Tb, E, sW + F.w_off[6], lane);
+        __syncwarp();
+        mma_static<32, 8, 32, 1, 8, 0, 0, 32, 0, 8, 0>(E, Tb, As + F.a_off[6], lane);
+        __syncwarp();
+      } else {
+        last_left_step<4>(E, Tb, sW + F.w_off[4], As + F.a_off[4], lane);
+        last_left_step<5>(E, Tb, sW + F.w_off[5], As + F.a_off[5], lane);
+        last_left_step<6>(E, Tb, sW + F.w_off[6], As + F.a_off[6], lane);
+      }
       last_left_step<7>(E, Tb, sW + F.w_off[7], As + F.a_off[7], lane);
       last_left_step<8>(E, Tb, sW + F.w_off[8], As + F.a_off[8], lane);
       // hairy site 9: a = 2, a' = 1, B = 32, B' = 1: H[s][B] = sum_a EL[a][B] A9[s][a];
@@ -1063,8 +1085,9 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
     if (!overlap_fast_plan(Pn, F)) return -1;
   }
   const bool mma = (nat || pad) && overlap_mma() && warps == 8;
+  const bool lmma = last && overlap_mma();
   overlap_prep_kernel<float><<<1, 1024, 0, st>>>(reinterpret_cast<const float*>(P.clf), P, F, small_w, wc,
-                                                 mma ? 4 : -1);
+                                                 lmma ? 0x60u : (mma ? 0x10u : 0u));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const size_t smem = wbytes + tabbytes + (size_t)warps * PER_WARP * 4;
@@ -1080,11 +1103,15 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(overlap_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(overlap_fast_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t need = (P.N + warps - 1) / warps;
   const int grid = (int)(need < sms ? need : sms);
-  if (last)
+  if (lmma)
+    overlap_fast_kernel<5><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+  else if (last)
     overlap_fast_kernel<4><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   else if (mma && pad)
     overlap_fast_kernel<3><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);

@@ -252,6 +252,18 @@ def test_alternative_code_paths_agree(gpu_lib, option):
             assert _state_err(a, b) < 1e-5
         if both:
             assert np.abs(ov_new - ov_old).max() <= 1e-5 * ov_old.max()
+    if option.startswith("ov_"):
+        # the last-site-hairy classifier (fMPO.compress_one_site) has its own static / tensor-core modes
+        clf9 = random_classifier(10, 32, centre=9, seed=5)
+        for D in (32, 10):
+            enc = gpu_lib.encode_images(imgs, D)
+            ov_new = gpu_lib.label_overlaps(enc, clf9)
+            batched.set_option(option, 0)
+            try:
+                ov_old = gpu_lib.label_overlaps(enc, clf9)
+            finally:
+                batched.set_option(option, 1)
+            assert np.abs(ov_new - ov_old).max() <= 1e-5 * ov_old.max()
 
 
 def test_encoding_does_not_depend_on_batch_composition(gpu_lib):
