@@ -110,7 +110,7 @@ def test_predictions_match_reference_fixtures(gpu_lib, golden, dtype, name):
 
 
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
-@pytest.mark.parametrize("D_enc,D_clf,centre", [(32, 32, 5), (10, 32, 5), (4, 8, 5), (32, 36, 9), (16, 20, 9), (2, 2, 5), (32, 32, 9), (10, 32, 9), (20, 32, 5)])
+@pytest.mark.parametrize("D_enc,D_clf,centre", [(32, 32, 5), (10, 32, 5), (4, 8, 5), (32, 36, 9), (16, 20, 9), (2, 2, 5), (32, 32, 9), (10, 32, 9), (20, 32, 5), (3, 32, 5), (7, 32, 9), (12, 16, 5), (32, 16, 9)])
 def test_overlap_kernel_matches_chain_oracle(gpu_lib, dtype, D_enc, D_clf, centre):
     """Overlap kernel alone: feed it the GPU's own MPS and compare with the
     oracle contraction of the same site tensors (gauge-proof)."""
