@@ -325,9 +325,9 @@ def main():
             "e2e_u8": {"value": world * N * args.steps / (e2e_u8_ms * 1e-3), "unit": "images/s",
                        "h2d_bytes_per_step": int(N * 784), "d2h_bytes_per_step": int(N * (16 * 4 + 4)),
                        "host_input": "uint8 pixels (MNIST's native type), pinned; /255 in the encoder load"},
-            # per step: 10 encode kernels per 131,072-image chunk (Gram | steps 0-3 | 3 x counting sort |
-            # step 4 | step 5 | step 6 | step 7 | steps 8-9) + overlap prep + overlap + count
-            "gpu_launches": (10 * ((N + 131071) // 131072) + 3) * args.steps,
+            # per step: 12 encode kernels per 131,072-image chunk (Gram | steps 0-3 | 3 x counting sort |
+            # step 4 | step 5 in three parts | step 6 | step 7 | steps 8-9) + overlap prep + overlap + count
+            "gpu_launches": (12 * ((N + 131071) // 131072) + 3) * args.steps,
             "kernels_ms": {"encode": enc_ms, "overlap": ovl_ms,
                            "encode_launches": dict(zip(["gram_steps_0_3", "sort", "step4", "step5", "tail_6_9"],
                                                        launch_ms))},

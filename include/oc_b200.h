@@ -61,6 +61,7 @@ const char* oc_last_error(void);
  *   "enc_pack" = 0  step 4 with 16 lanes per image instead of packed warps
  *   "enc_mgs4" = 0  step 4 without the Gram-Schmidt preconditioning
  *   "enc_qr5"  = 0  step 5 without the pivoted Gram-Schmidt preconditioning
+ *   "enc_split5" = 0  step 5 as one kernel instead of three
  *   "enc_sort" = 0  no device-side sort of the images by live rows
  *   "ov_static" = 0 run-time shapes in the overlap kernel for the 32/32 profile
  *   "ov_mma"   = 0  FFMA instead of tensor-core contractions in the overlap kernel

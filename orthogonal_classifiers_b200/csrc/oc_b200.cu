@@ -119,6 +119,10 @@ int oc_set_option(const char* key, int value) {
     oc::overlap_static_shapes() = value;
     return OC_OK;
   }
+  if (key && !strcmp(key, "enc_split5")) {
+    oc::hw::split_step5() = value;
+    return OC_OK;
+  }
   if (key && !strcmp(key, "enc_qr5")) {
     oc::hw::qr_step5() = value;
     return OC_OK;

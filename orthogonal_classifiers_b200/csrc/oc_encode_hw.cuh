@@ -1315,11 +1315,19 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col_kernel(const
 // of Gram-Schmidt projections (smaller sigma against larger, as in the row steps)
 // restores (numpy model: 6e-4 -> 2e-7).  NE = packed pairs per lane and column:
 // 13 when rows l >= 26 of Psi_5 are structurally zero (n_pix <= 832), else 16.
-template <int NE>
+// PART 0: the whole step in one kernel.  PART 1 / (hw_col5b_kernel) / PART 3: the same cut in
+// three - Gram-Schmidt | 16 x 16 Jacobi | U, polish, A_5 - so that the Jacobi, which is all
+// rotation-parameter chain, runs with ONE lane per slot and four images per warp instead of
+// two lanes per slot computing every chain twice.  R, then the converged vectors, their norms and
+// ranks travel through the free part of the image's Psi_6 slot in the workspace:
+//   floats 0..255 Psi_6 | 256..511 R / converged vectors | 512 thr2 | 513 nsteps | 514 sweeps |
+//   520..535 squared norms | 536..551 ranks
+constexpr int kC5R = 256, kC5Meta = 512, kC5N2 = 520, kC5Rank = 536;
+template <int NE, int PART = 0>
 __global__ void __launch_bounds__(kHwWarps * 32, 4)
 hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict__ ws_in, float* __restrict__ ws_out) {
   constexpr int Q = 16;
-  __shared__ __align__(16) float Rsm[kHwWarps * 2 * 256];
+  __shared__ __align__(16) float Rsm[PART == 0 ? kHwWarps * 2 * 256 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lg = lane & 15, hb = lane & 16, h = lane >> 4;
   const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
@@ -1327,11 +1335,15 @@ hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
   const int64_t im = valid ? img : 0;
   const float* psi = ws_in + (size_t)im * kWsStride;  // [32][2Q]
   const int slot = lg >> 1, sub = lg & 1;
-  float* R = Rsm + (size_t)(warp * 2 + h) * 256;  // R[step][column]
+  float* slot6 = ws_out + (size_t)im * kWsStride;  // Psi_6 slot of the image (PART != 0: R and meta too)
+  float* R = PART == 0 ? Rsm + (size_t)(warp * 2 + h) * 256 : slot6 + kC5R;  // R[step][column]
   // lane's elements: (s = sub, l = 0 .. 2 NE - 1); packed pair j = (l = 2j, 2j + 1)
   u64 T[16], S[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) T[j] = S[j] = 0ull;
+  float nT = 0.f, nS = 0.f, thr2 = 0.f;
+  int nsteps = 0;  // R rows up to the last live pivot
+  if constexpr (PART != 3) {
   {
     const float* pc = psi + sub * Q + 2 * slot;
 #pragma unroll
@@ -1345,11 +1357,11 @@ hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
       S[j] = pack2(v0.y, v1.y);
     }
   }
-  float nT = dot16<1, NE>(T, T), nS = dot16<1, NE>(S, S);
+  nT = dot16<1, NE>(T, T);
+  nS = dot16<1, NE>(S, S);
   const float fro = group_sum<4>(sub == 0 ? nT + nS : 0.f);
-  const float thr2 = kFloor2 * fro;
-  // ---- column-pivoted MGS; R[step][c] -> shared ----
-  int nsteps = 0;  // R rows up to the last live pivot
+  thr2 = kFloor2 * fro;
+  // ---- column-pivoted MGS; R[step][c] -> shared (PART 1: workspace) ----
   {
 #pragma unroll 1
     for (int step = 0; step < Q; ++step) {
@@ -1387,7 +1399,7 @@ hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
         T[e] = fma2(cT2, qv[e], T[e]);
         S[e] = fma2(cS2, qv[e], S[e]);
       }
-      if (sub == 0) {
+      if (sub == 0 && (PART == 0 || valid)) {
         const float dg = qn2 * invn;
         *reinterpret_cast<float2*>(R + step * Q + 2 * slot) =
             make_float2(isT ? dg : rT * invn, isS ? dg : rS * invn);
@@ -1398,34 +1410,52 @@ hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
       if (!dead) nsteps = step + 1;
     }
   }
+  }  // PART != 3
+  if constexpr (PART == 1) {
+    if (valid && lg == 0) {
+      slot6[kC5Meta] = thr2;
+      reinterpret_cast<int*>(slot6)[kC5Meta + 1] = nsteps;
+    }
+    return;
+  }
   __syncwarp();
   // ---- Jacobi on the rows of R (vector j = R[j][.], 8 elements per lane) ----
 #pragma unroll
   for (int j = 0; j < 16; ++j) T[j] = S[j] = 0ull;
-  {
-    const float* r0 = R + (2 * slot) * Q + 8 * sub;
-    const float4 a0 = lds4(r0), a1 = lds4(r0 + 4), b0 = lds4(r0 + Q), b1 = lds4(r0 + Q + 4);
+  if (PART == 0 || valid) {
+    const float* r0 = R + (2 * slot) * Q + 8 * sub;  // PART 3: the converged vectors hw_col5b_kernel left here
+    const float4 a0 = ld4<PART != 0>(r0), a1 = ld4<PART != 0>(r0 + 4), b0 = ld4<PART != 0>(r0 + Q),
+                 b1 = ld4<PART != 0>(r0 + Q + 4);
     T[0] = pack2(a0.x, a0.y); T[1] = pack2(a0.z, a0.w); T[2] = pack2(a1.x, a1.y); T[3] = pack2(a1.z, a1.w);
     S[0] = pack2(b0.x, b0.y); S[1] = pack2(b0.z, b0.w); S[2] = pack2(b1.x, b1.y); S[3] = pack2(b1.z, b1.w);
   }
-  nT = dot16<1, 4>(T, T);
-  nS = dot16<1, 4>(S, S);
+  int sweeps = 0, rT = 0, rS = 0;
+  if constexpr (PART == 3) {
+    thr2 = valid ? slot6[kC5Meta] : 0.f;
+    nsteps = valid ? reinterpret_cast<const int*>(slot6)[kC5Meta + 1] : 0;
+    nT = valid ? slot6[kC5N2 + 2 * slot] : 0.f;
+    nS = valid ? slot6[kC5N2 + 2 * slot + 1] : 0.f;
+    rT = valid ? reinterpret_cast<const int*>(slot6)[kC5Rank + 2 * slot] : 2 * slot;
+    rS = valid ? reinterpret_cast<const int*>(slot6)[kC5Rank + 2 * slot + 1] : 2 * slot + 1;
+  }
   const int mlive = (nsteps + 1) >> 1;
   int mlive_max = mlive;
   mlive_max = max(mlive_max, __shfl_xor_sync(FULL, mlive_max, 16));
-  int sweeps = 0;
-  if (mlive_max > 0) {
-    sweeps = jacobi16<1, 4, 4>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+  if constexpr (PART == 0) {
     nT = dot16<1, 4>(T, T);
     nS = dot16<1, 4>(S, S);
+    if (mlive_max > 0) {
+      sweeps = jacobi16<1, 4, 4>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+      nT = dot16<1, 4>(T, T);
+      nS = dot16<1, 4>(S, S);
+    }
+    rank16<1, 4>(nT, nS, lane, rT, rS);
   }
-  int rT, rS;
-  rank16<1, 4>(nT, nS, lane, rT, rS);
   const Out io = make_out(P, im, 5);
   const int r_rt = io.r_rt, b_rt = io.b_rt;
   const bool kT = nT > thr2 && rT < r_rt;
   const bool kS = nS > thr2 && rS < r_rt;
-  if (valid) {
+  if (PART == 0 && valid) {
     if (io.sv) {
       if (sub == 0) {
         if (rT < io.sv_width) io.sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
@@ -1502,7 +1532,7 @@ hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
     // columns with sigma < 3e-5 sigma_max start ~1e-2 off, and what one pass leaves between two of
     // them is second order in that (1e-3 measured on low-contrast images): two more passes, only for
     // warps that have such columns (none on MNIST-like data)
-    const bool tiny = (keyT > 0.f && keyT < 1e-9f * fro) || (keyS > 0.f && keyS < 1e-9f * fro);
+    const bool tiny = (keyT > 0.f && keyT < 1e3f * thr2) || (keyS > 0.f && keyS < 1e3f * thr2);  // sigma^2 < 1e-9 |M|_F^2
     if (__any_sync(FULL, tiny)) {
       polish16<1, NE, true>(UT, US, keyT, keyS, tagT, tagS, lane, mlive, mlive_max);
       polish16<1, NE, true>(UT, US, keyT, keyS, tagT, tagS, lane, mlive, mlive_max);
@@ -1540,6 +1570,68 @@ hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
         for (int e = lg; e < 2 * nz; e += 16) io.A[((e / nz) * b_rt + 2 * NE) * r_rt + e % nz] = 0.f;
     }
   }
+}
+
+// ---- step 5, middle part: Jacobi on the rows of R with one lane per slot, 4 images per warp ----
+__global__ void __launch_bounds__(kHwWarps * 32, 6)
+hw_col5b_kernel(const __grid_constant__ EncodeParams P, float* __restrict__ ws_out) {
+  constexpr int Q = 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sl = lane & 7;
+  const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 4 + (lane >> 3);
+  const bool valid = img < P.N;
+  const int64_t im = valid ? img : 0;
+  float* slot6 = ws_out + (size_t)im * kWsStride;
+  float* r0 = slot6 + kC5R + (2 * sl) * Q;
+  u64 A[8], Bv[8];
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
+    if (valid) {
+      a = *reinterpret_cast<const float4*>(r0 + 4 * q4);
+      bq = *reinterpret_cast<const float4*>(r0 + Q + 4 * q4);
+    }
+    A[2 * q4] = pack2(a.x, a.y); A[2 * q4 + 1] = pack2(a.z, a.w);
+    Bv[2 * q4] = pack2(bq.x, bq.y); Bv[2 * q4 + 1] = pack2(bq.z, bq.w);
+  }
+  const float thr2 = valid ? slot6[kC5Meta] : 0.f;
+  const int nsteps = valid ? reinterpret_cast<const int*>(slot6)[kC5Meta + 1] : 0;
+  float nA = dot16<0, 8>(A, A), nB = dot16<0, 8>(Bv, Bv);
+  const int ml = (nsteps + 1) >> 1;
+  const int mlmax = __reduce_max_sync(FULL, ml);
+  int sw = 0;
+  if (mlmax > 0) {
+    sw = jacobi_ring<8>(A, Bv, nA, nB, thr2, lane, 8, lane & ~7, ml, mlmax);
+    nA = dot16<0, 8>(A, A);
+    nB = dot16<0, 8>(Bv, Bv);
+  }
+  int rA, rB;
+  rank16<0, 3>(nA, nB, lane, rA, rB);
+  if (!valid) return;
+  const Out io = make_out(P, im, 5);
+  const bool kA = nA > thr2 && rA < io.r_rt, kB = nB > thr2 && rB < io.r_rt;
+  if (io.sv) {
+    if (rA < io.sv_width) io.sv[rA] = nA > thr2 ? sqrtf(nA) : 0.f;
+    if (rB < io.sv_width) io.sv[rB] = nB > thr2 ? sqrtf(nB) : 0.f;
+    for (int k = Q + sl; k < io.sv_width; k += 8) io.sv[k] = 0.f;
+  }
+  if (io.sweeps && sl == 0) *io.sweeps = sw;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    float4 a, bq;
+    unpack2(A[2 * q4], a.x, a.y); unpack2(A[2 * q4 + 1], a.z, a.w);
+    unpack2(Bv[2 * q4], bq.x, bq.y); unpack2(Bv[2 * q4 + 1], bq.z, bq.w);
+    // the converged vectors for the third part, and as rows of Psi_6 (sigma_r v_r)
+    *reinterpret_cast<float4*>(r0 + 4 * q4) = a;
+    *reinterpret_cast<float4*>(r0 + Q + 4 * q4) = bq;
+    if (rA < Q) *reinterpret_cast<float4*>(slot6 + rA * Q + 4 * q4) = kA ? a : z;
+    if (rB < Q) *reinterpret_cast<float4*>(slot6 + rB * Q + 4 * q4) = kB ? bq : z;
+  }
+  slot6[kC5N2 + 2 * sl] = nA;
+  slot6[kC5N2 + 2 * sl + 1] = nB;
+  reinterpret_cast<int*>(slot6)[kC5Rank + 2 * sl] = rA;
+  reinterpret_cast<int*>(slot6)[kC5Rank + 2 * sl + 1] = rB;
 }
 
 // ---- steps 8 and 9, one THREAD per image: Psi_8 is 4 x 4 ----
@@ -1678,6 +1770,10 @@ inline int& qr_step5() {
   static int v = 1;
   return v;
 }
+inline int& split_step5() {
+  static int v = 1;
+  return v;
+}
 inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, void* sort_ws, int64_t chunk,
                                 int sms, cudaStream_t st) {
   const int per_cta = kHwWarps * 2;
@@ -1737,7 +1833,15 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
     hw_row_kernel<4, false, false><<<grid, kHwWarps * 32, smem4, st>>>(P, ws1, ws0, nullptr, nullptr, nullptr);
   }
   ee.mark(3, st);
-  if (qr_step5() && P.n_pix <= 832)
+  if (qr_step5() && split_step5()) {
+    // Gram-Schmidt | 16 x 16 Jacobi (4 images per warp) | U, polish, A_5
+    const int gridb = (int)((P.N + 4 * kHwWarps - 1) / (4 * kHwWarps));
+    if (P.n_pix <= 832) hw_col5q_kernel<13, 1><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
+    else hw_col5q_kernel<16, 1><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
+    hw_col5b_kernel<<<gridb, kHwWarps * 32, 0, st>>>(P, ws1);
+    if (P.n_pix <= 832) hw_col5q_kernel<13, 3><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
+    else hw_col5q_kernel<16, 3><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
+  } else if (qr_step5() && P.n_pix <= 832)
     hw_col5q_kernel<13><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
   else if (qr_step5())
     hw_col5q_kernel<16><<<grid, kHwWarps * 32, 0, st>>>(P, ws0, ws1);
