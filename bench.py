@@ -13,12 +13,19 @@ collective is a 16-byte all-reduce of (correct, total).
 import argparse
 import json
 import os
-import subprocess
-import sys
-import threading
-import time
 
-import numpy as np
+# one BLAS/OpenMP thread per process, set before numpy loads: the CPU arm runs one worker
+# process per host core; threaded BLAS inside each of them would oversubscribe the cores
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
+
+import subprocess  # noqa: E402
+import sys  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
