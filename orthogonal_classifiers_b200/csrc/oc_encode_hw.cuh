@@ -1337,6 +1337,14 @@ hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
   const int slot = lg >> 1, sub = lg & 1;
   float* slot6 = ws_out + (size_t)im * kWsStride;  // Psi_6 slot of the image (PART != 0: R and meta too)
   float* R = PART == 0 ? Rsm + (size_t)(warp * 2 + h) * 256 : slot6 + kC5R;  // R[step][column]
+  if constexpr (PART == 3) {
+    // M_5 is first needed after a dependent round trip for the Jacobi results: start its
+    // 2 NE rows of 128 B towards L2 now (lane lg takes rows 2 lg, 2 lg + 1)
+    if (valid && lg < NE) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(psi + (2 * lg) * 2 * Q));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(psi + (2 * lg + 1) * 2 * Q));
+    }
+  }
   // lane's elements: (s = sub, l = 0 .. 2 NE - 1); packed pair j = (l = 2j, 2j + 1)
   u64 T[16], S[16];
 #pragma unroll

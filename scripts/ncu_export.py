@@ -1,9 +1,10 @@
-"""Key metrics of the first kernel in an .ncu-rep as `metric,unit,value` lines:
-python scripts/ncu_export.py report.ncu-rep > profiles/xxx.csv"""
+"""Key metrics of one kernel (the first, or the k-th with a second argument) in an
+.ncu-rep as `metric,unit,value` lines:
+python scripts/ncu_export.py report.ncu-rep [k] > profiles/xxx.csv"""
 import csv, io, subprocess, sys
 out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units, vals = rows[0], rows[1], rows[2 + (int(sys.argv[2]) if len(sys.argv) > 2 else 0)]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
