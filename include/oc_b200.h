@@ -63,6 +63,9 @@ const char* oc_last_error(void);
  *   "enc_qr5"  = 0  step 5 without the pivoted Gram-Schmidt preconditioning
  *   "enc_split5" = 0  step 5 as one kernel instead of three
  *   "enc_sort" = 0  no device-side sort of the images by live rows
+ *   "enc_split2" = 1  (opt-in) the two halves of an encoder chunk of >= 32,768 images
+ *                   on two streams, rejoined on the caller's stream before return;
+ *                   bit-identical results, ignored while "enc_events" is on
  *   "ov_static" = 0 run-time shapes in the overlap kernel for the 32/32 profile
  *   "ov_mma"   = 0  FFMA instead of tensor-core contractions in the overlap kernel
  *   "ov_pad"   = 0  D_encode < 32 images through the run-time-shaped overlap kernel

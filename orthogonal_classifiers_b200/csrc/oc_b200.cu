@@ -119,6 +119,10 @@ int oc_set_option(const char* key, int value) {
     oc::overlap_static_shapes() = value;
     return OC_OK;
   }
+  if (key && !strcmp(key, "enc_split2")) {
+    oc::encode_split2() = value;
+    return OC_OK;
+  }
   if (key && !strcmp(key, "enc_split5")) {
     oc::hw::split_step5() = value;
     return OC_OK;
@@ -214,7 +218,7 @@ int oc_encode_batch(const void* images_dev, int in_dtype, int64_t N, int n_pix, 
     float* ws = nullptr;
     {
       std::lock_guard<std::mutex> lk(g_ws_mu);
-      if (int rc = g_enc_ws.ensure((size_t)2 * chunk * oc::kWsStride * sizeof(float) + oc::encode_sort_bytes(chunk))) return rc;
+      if (int rc = g_enc_ws.ensure((size_t)2 * chunk * oc::kWsStride * sizeof(float) + 2 * oc::encode_sort_bytes(chunk) + 512)) return rc;
       ws = reinterpret_cast<float*>(g_enc_ws.p);
     }
     int rc = oc::encode_fast_launch(P, ws, num_sms(), st);

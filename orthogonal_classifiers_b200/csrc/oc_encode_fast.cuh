@@ -614,6 +614,19 @@ inline int& encode_use_hw() {
   static int v = 1;
   return v;
 }
+// opt-in (oc_set_option("enc_split2", 1)): halves of a chunk on two streams
+inline int& encode_split2() {
+  static int v = 0;
+  return v;
+}
+struct SplitStreams {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+inline SplitStreams& split_streams() {
+  static SplitStreams s;
+  return s;
+}
 namespace hw {
 inline bool supported(const EncodeParams& P);
 inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, void* sort_ws, int64_t chunk,
@@ -644,7 +657,36 @@ inline int encode_fast_launch(const EncodeParams& P0, float* ws, int sms, cudaSt
       ~Restore() { encode_events().on = v; }
     } restore{ev_on};
     if (encode_use_hw() && hw::supported(P)) {
-      e = hw::launch_chain(P, ws0, ws1, ws + (size_t)2 * chunk * kWsStride, chunk, sms, st);
+      char* sort_ws = reinterpret_cast<char*>(ws + (size_t)2 * chunk * kWsStride);
+      if (encode_split2() && !ev_on && P.N >= 32768) {
+        // two halves of the chunk on two streams: the CTAs of one half fill the SMs that the
+        // last wave of the other half's kernel leaves idle (a Jacobi CTA lives 100-200 us)
+        SplitStreams& ss = split_streams();
+        if (!ss.aux) {
+          if ((e = cudaStreamCreateWithFlags(&ss.aux, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+          cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);
+          cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming);
+        }
+        const int64_t nA = ((P.N / 2) + 63) & ~(int64_t)63;
+        EncodeParams PA = P, PB = P;
+        PA.N = nA;
+        PB.N = P.N - nA;
+        PB.images = reinterpret_cast<const char*>(P.images) + (size_t)nA * P0.ld * in_esz;
+        PB.mps_out = reinterpret_cast<float*>(P.mps_out) + (size_t)nA * P0.mps_stride;
+        if (P.svals_out) PB.svals_out = reinterpret_cast<float*>(P.svals_out) + (size_t)nA * P0.L * P0.sv_width;
+        if (P.sweeps_out) PB.sweeps_out = P.sweeps_out + (size_t)nA * P0.L;
+        cudaEventRecord(ss.fork, st);
+        cudaStreamWaitEvent(ss.aux, ss.fork, 0);
+        e = hw::launch_chain(PB, ws0 + (size_t)nA * kWsStride, ws1 + (size_t)nA * kWsStride,
+                             sort_ws + ((encode_sort_bytes(chunk) + 255) & ~(size_t)255), chunk, sms, ss.aux);
+        if (e != cudaSuccess) return (int)e;
+        e = hw::launch_chain(PA, ws0, ws1, sort_ws, chunk, sms, st);
+        if (e != cudaSuccess) return (int)e;
+        cudaEventRecord(ss.join, ss.aux);
+        cudaStreamWaitEvent(st, ss.join, 0);
+        continue;
+      }
+      e = hw::launch_chain(P, ws0, ws1, sort_ws, chunk, sms, st);
       if (e != cudaSuccess) return (int)e;
       continue;
     }

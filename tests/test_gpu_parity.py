@@ -266,6 +266,31 @@ def test_alternative_code_paths_agree(gpu_lib, option):
             assert np.abs(ov_new - ov_old).max() <= 1e-5 * ov_old.max()
 
 
+@pytest.mark.gpu
+def test_two_stream_chunk_split_is_bit_identical(gpu_lib):
+    """``enc_split2`` (opt-in): the two halves of an encoder chunk run on two
+    streams and rejoin the caller's stream.  An image's MPS does not depend on
+    which other images share its kernel launch, so MPS, singular values,
+    overlaps and labels must be bit-identical to the single-stream chain."""
+    import torch
+    from orthogonal_classifiers_b200 import batched
+    base = np.concatenate([synthetic_images(2041, seed=33), adversarial_images()]).astype(np.float32)
+    imgs = torch.from_numpy(np.tile(base, (20, 1))[:40001]).cuda()   # >= 32,768: the split engages; odd size
+    clf = gpu_lib.DeviceClassifier(random_classifier(10, 32, centre=5, seed=6))
+    ref = gpu_lib.encode_images(imgs, 32, return_svals=True)
+    ov_ref, am_ref = batched.overlaps_from_mps(ref, clf)
+    batched.set_option("enc_split2", 1)
+    try:
+        new = gpu_lib.encode_images(imgs, 32, return_svals=True)
+        ov_new, am_new = batched.overlaps_from_mps(new, clf)
+        torch.cuda.synchronize()
+    finally:
+        batched.set_option("enc_split2", 0)
+    assert torch.equal(new.data, ref.data)
+    assert torch.equal(new.svals, ref.svals)
+    assert torch.equal(ov_new, ov_ref) and torch.equal(am_new, am_ref)
+
+
 def test_encoding_does_not_depend_on_batch_composition(gpu_lib):
     """Images share warps (two per warp in most kernels, up to four of equal
     live-row count in the packed step 4, chosen by a device-side counting sort
