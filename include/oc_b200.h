@@ -9,6 +9,14 @@
  * (a cudaStream_t passed as void*, NULL = default stream) and performs no
  * hidden synchronisation unless stated.  No torch types appear here.
  *
+ * Library state.  Scratch memory, the re-laid classifier and auxiliary streams
+ * live in a context keyed by (current device, stream): calls on different
+ * streams or devices share nothing; host threads calling on the SAME stream are
+ * serialised by a mutex.  Scratch of the device-pointer entry points grows with
+ * cudaMallocAsync / cudaFreeAsync on the call's stream (stream-ordered, never a
+ * device-wide synchronisation).  oc_release() frees a context.  The switches of
+ * oc_set_option are process-global diagnostics, not per-call state.
+ *
  * Return value: 0 = OK, non-zero = error (OC_E_*); the message is available
  * from oc_last_error() (thread-local).
  *
@@ -44,7 +52,11 @@ extern "C" {
 #define OC_E_CAPACITY 4 /* output buffer too small */
 
 /* encoder variants: which sweep applies the D truncation */
-#define OC_TRUNC_INLINE 0 /* truncate inside the left-to-right SVD chain */
+#define OC_TRUNC_INLINE 0 /* truncate inside the left-to-right SVD chain (BASELINE.json's wording) */
+#define OC_TRUNC_SWEEP 1  /* exact chain, RIGHT-TO-LEFT truncating sweep, sweep back to the left-canonical
+                           * gauge: the order of xmps' left_from_state(..).left_canonicalise(D) as called at
+                           * tools.py:221 (restated in oracle/stubs/xmps/fMPS.py).  Identical to INLINE
+                           * when D truncates no bond (D >= 2^floor(L/2), e.g. D >= 32 for 28x28 images). */
 
 #define OC_MAX_L 10      /* n_pix <= 1024 */
 #define OC_MAX_SITES 64  /* overlap kernel: chain length (MPS stacking) */
@@ -71,6 +83,8 @@ const char* oc_last_error(void);
  *   "ov_pad"   = 0  D_encode < 32 images through the run-time-shaped overlap kernel
  *                   instead of zero-padded through the 32/32 one
  *   "enc_events"    see oc_encode_step_ms
+ *   "host_chunk" = n  images per pipeline stage of oc_classify_host (0 = default: 17,500 for
+ *                   float pixels, 35,000 for uint8)
  * Unknown keys return OC_E_ARG. */
 int oc_set_option(const char* key, int value);
 
@@ -92,8 +106,12 @@ int oc_svals_width(int L, int D);
  *                OC_F32 | OC_F64 | OC_U8
  *   dtype        arithmetic + output type, OC_F32 | OC_F64
  *   mps_out_dev  N * site_offsets[L] elements of `dtype`
+ *   trunc_mode   OC_TRUNC_INLINE | OC_TRUNC_SWEEP
  *   svals_out_dev  nullable; N * L * oc_svals_width() elements: the singular
- *                values found at step n (bond n+1), descending, zero padded
+ *                values found at step n (bond n+1), descending, zero padded.
+ *                OC_TRUNC_SWEEP: row n holds what the right-to-left sweep saw at
+ *                bond n+1 (the image already truncated on the bonds to its right),
+ *                row L-1 the norm of the truncated image
  *   sweeps_out_dev nullable; N * L int32 Jacobi sweep counts (diagnostics)
  * An all-zero image yields an all-zero MPS (the reference would fail). */
 int oc_encode_batch(const void* images_dev, int in_dtype, int64_t N, int n_pix,
@@ -129,6 +147,17 @@ int oc_encode_classify(const void* images_dev, int in_dtype, int64_t N,
                        void* workspace_dev, void* overlaps_out_dev,
                        int32_t* argmax_out_dev, void* stream);
 
+/* Optional: declare the packed classifier at clf_dev immutable (enable = 1) so that
+ * oc_overlap_batch / oc_encode_classify on this stream re-lay it for the kernel once
+ * instead of on every call; enable = 1 again after changing its contents, enable = 0
+ * before freeing it.  Without this call every overlap launch is preceded by a ~20 us
+ * re-layout kernel. */
+int oc_classifier_cache(const void* clf_dev, int enable, void* stream);
+
+/* Free the scratch, cached classifiers and auxiliary streams of the context
+ * (current device, stream).  Stream-ordered for the device-pointer scratch. */
+int oc_release(void* stream);
+
 /* The integer part of variational_mpo_classifiers.py:340-345 (k = 1):
  * out2_dev[0] += #(argmax == label), out2_dev[1] += N.  The caller zeroes
  * out2_dev; across ranks the two int64 are summed with one NCCL all-reduce. */
@@ -151,10 +180,14 @@ int oc_pack_classifier(const void* const* site_ptrs_host,
                        int dtype, void* packed_out_host, int64_t capacity,
                        int64_t* n_written, int32_t* bonds_out, int32_t* s_out);
 
-/* End-to-end convenience with HOST buffers (what a reference user holds):
- * copies the images to the device, encodes, classifies, copies |overlaps| and
- * argmax back, synchronises `stream`.  Device scratch is kept grow-only inside
- * the library.  images_host may be pageable or pinned. */
+/* End-to-end call with HOST buffers (what a reference user holds): images in
+ * (float32 / float64 / uint8 as MNIST ships them, tools.py:25-74 divides by 255),
+ * |overlaps| and argmax out.  The batch is cut into chunks; the host->device copy
+ * of chunk k+1 (own copy stream) runs under the kernels of chunk k (`stream`) and
+ * the results return on a third stream; the call returns after synchronising
+ * `stream`.  Staging buffers are grow-only inside the context (plain cudaMalloc:
+ * growing synchronises the device; sizes settle after the first call).  Copies
+ * overlap only when the host buffers are pinned; pageable memory works, slower. */
 int oc_classify_host(const void* images_host, int in_dtype, int64_t N,
                      int n_pix, int64_t ld, int L, int D, int dtype,
                      int trunc_mode, const void* clf_packed_host,

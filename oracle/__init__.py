@@ -29,6 +29,7 @@ from .mps_oracle import (  # noqa: F401
     encode_image,
     mps_to_state,
     bond_singular_values,
+    sweep_singular_values,
     overlaps_chain,
     dense_classifier,
     overlaps_dense,

@@ -146,6 +146,21 @@ def encode_image(f_image: np.ndarray, D: int | None, variant: str = "inline",
     raise ValueError(f"unknown variant {variant!r}")
 
 
+def sweep_singular_values(f_image: np.ndarray, D: int | None, trim: bool = True) -> list[np.ndarray]:
+    """What the right-to-left truncating sweep of variant "sweep" sees, in the
+    convention of ``oc_encode_batch(..., OC_TRUNC_SWEEP, svals_out)``: entry n
+    (bond n+1, n = 0..L-2) = the singular values the sweep finds at site n+1 —
+    those of the image already truncated on the bonds to the right — scaled to
+    the UNNORMALISED image; entry L-1 = the norm of the truncated image."""
+    x, L = pad_image(f_image)
+    nrm = np.linalg.norm(x)
+    sites, _, _ = _tt_svd(x, L, None, trim)
+    swept, schmidt = _right_sweep_truncate(sites, D, trim)
+    out = [nrm * schmidt[n + 1] for n in range(L - 1)]
+    out.append(np.array([nrm * np.linalg.norm(swept[0])]))
+    return out
+
+
 def mps_to_state(sites) -> np.ndarray:
     """Contract an MPS (list of (2, Dl, Dr)) to its 2^L amplitude vector,
     site 0 = most significant bit of the flat index (C-order reshape,

@@ -10,6 +10,7 @@ from .batched import (  # noqa: F401
     HostPipeline,
     MPSBatch,
     classify,
+    classify_host,
     count_correct,
     encode_images,
     evaluate,

@@ -9,6 +9,8 @@ from .build import LIB
 
 OC_F32, OC_F64, OC_U8 = 0, 1, 2
 OC_TRUNC_INLINE = 0
+OC_TRUNC_SWEEP = 1
+TRUNC = {"inline": OC_TRUNC_INLINE, "sweep": OC_TRUNC_SWEEP}
 OC_MAX_L = 10
 OC_MAX_SITES = 64
 
@@ -16,6 +18,7 @@ EXPORTS = [
     "oc_version", "oc_last_error", "oc_set_option", "oc_mps_layout", "oc_svals_width",
     "oc_encode_batch", "oc_overlap_batch", "oc_encode_classify", "oc_count_correct",
     "oc_pack_classifier", "oc_classify_host", "oc_fma_peak_launch", "oc_encode_step_ms",
+    "oc_classifier_cache", "oc_release",
 ]
 
 
@@ -46,6 +49,8 @@ def _load():
     lib.oc_pack_classifier.argtypes = [C.POINTER(vp), p32, i32, i32, i32, vp, i64, p64, p32, p32]
     lib.oc_classify_host.argtypes = [vp, i32, i64, i32, i64, i32, i32, i32, i32, vp, i64, p32, p32,
                                      vp, vp, vp]
+    lib.oc_classifier_cache.argtypes = [vp, i32, vp]
+    lib.oc_release.argtypes = [vp]
     lib.oc_fma_peak_launch.argtypes = [i64, vp, C.POINTER(C.c_double), vp]
     lib.oc_encode_step_ms.argtypes = [C.POINTER(C.c_float), C.c_int]
     for name in EXPORTS:

@@ -14,7 +14,23 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import OC_F32, OC_F64, OC_U8, check, i32_array, lib
+from ._lib import OC_F32, OC_F64, OC_U8, TRUNC, check, i32_array, lib
+
+# Which sweep applies the D_encode truncation (include/oc_b200.h).  "sweep" follows
+# the reference's call order at tools.py:221 — left_from_state(...) exact, then
+# left_canonicalise(D): right-to-left truncating sweep, sweep back — and is the default of every
+# reference-named entry point; "inline" truncates inside the left-to-right chain (BASELINE.json's
+# wording).  The two coincide whenever D truncates nothing (D >= 32 for 28 x 28 images).
+DEFAULT_TRUNC = "sweep"
+
+
+def _trunc(trunc) -> int:
+    if trunc is None:
+        trunc = DEFAULT_TRUNC
+    try:
+        return TRUNC[trunc]
+    except KeyError:
+        raise ValueError(f"trunc must be 'sweep' or 'inline', got {trunc!r}") from None
 
 _TORCH_DT = {"f32": torch.float32, "f64": torch.float64}
 _OC_DT = {"f32": OC_F32, "f64": OC_F64}
@@ -132,9 +148,10 @@ class MPSBatch:
 
 
 def encode_images(images, D: int | None, dtype: str = "f32", return_svals: bool = False,
-                  return_sweeps: bool = False, device=None) -> MPSBatch:
+                  return_sweeps: bool = False, device=None, trunc: str | None = None) -> MPSBatch:
     """Batched ``mps_encoding`` (variational_mpo_classifiers.py:102-104):
-    every image -> unit-norm left-canonical MPS truncated to bond D."""
+    every image -> unit-norm left-canonical MPS truncated to bond D.
+    ``trunc``: "sweep" (default, the reference's order) or "inline"."""
     t = to_device_images(images, device)
     N, n_pix = t.shape
     L = n_sites_for(n_pix)
@@ -150,7 +167,7 @@ def encode_images(images, D: int | None, dtype: str = "f32", return_svals: bool 
     with torch.cuda.device(dev):
         check(lib.oc_encode_batch(
             t.data_ptr(), _in_dtype(t), N, n_pix, _ld(t), L, 0 if D is None else int(D),
-            _OC_DT[dtype], _lib.OC_TRUNC_INLINE, out.data_ptr(),
+            _OC_DT[dtype], _trunc(trunc), out.data_ptr(),
             svals.data_ptr() if svals is not None else None,
             sweeps.data_ptr() if sweeps is not None else None, _stream_ptr()))
     return MPSBatch(out, bonds, offs, L, D, dtype, svals, sweeps)
@@ -196,11 +213,34 @@ class DeviceClassifier:
         self._s_c = s
         self.device = _device(device)
         self.packed = torch.from_numpy(packed).to(self.device)
+        self._cached_on = set()
 
     def to(self, device) -> "DeviceClassifier":
+        self._uncache()
         self.device = _device(device)
         self.packed = self.packed.to(self.device)
         return self
+
+    def cache_on_stream(self, stream_ptr: int) -> None:
+        """Tell the library the packed buffer is immutable, so that the overlap kernel's
+        re-layout of it runs once per stream instead of once per call (oc_classifier_cache)."""
+        if stream_ptr in self._cached_on:
+            return
+        with torch.cuda.device(self.device):
+            check(lib.oc_classifier_cache(self.packed.data_ptr(), 1, stream_ptr))
+        self._cached_on.add(stream_ptr)
+
+    def _uncache(self) -> None:
+        for sp in list(getattr(self, "_cached_on", ())):
+            try:
+                with torch.cuda.device(self.device):
+                    lib.oc_classifier_cache(self.packed.data_ptr(), 0, sp)
+            except Exception:
+                pass
+        self._cached_on = set()
+
+    def __del__(self):
+        self._uncache()
 
 
 def _as_classifier(classifier, dtype: str, device=None) -> DeviceClassifier:
@@ -224,6 +264,7 @@ def overlaps_from_mps(mps: MPSBatch, classifier, return_argmax: bool = True):
     ov = torch.empty((N, clf.S), dtype=_TORCH_DT[mps.dtype], device=dev)
     am = torch.empty((N,), dtype=torch.int32, device=dev) if return_argmax else None
     with torch.cuda.device(dev):
+        clf.cache_on_stream(_stream_ptr())
         check(lib.oc_overlap_batch(
             mps.data.data_ptr(), i32_array(mps.bonds), clf.packed.data_ptr(), clf._bonds_c, clf._s_c,
             mps.L, N, _OC_DT[mps.dtype], ov.data_ptr(), am.data_ptr() if am is not None else None,
@@ -232,7 +273,7 @@ def overlaps_from_mps(mps: MPSBatch, classifier, return_argmax: bool = True):
 
 
 def classify_device(images_dev: torch.Tensor, clf: DeviceClassifier, D: int | None,
-                    workspace: torch.Tensor | None = None, out=None):
+                    workspace: torch.Tensor | None = None, out=None, trunc: str | None = None):
     """encode + classify with device-resident inputs; returns device tensors
     (overlaps (N, S), argmax (N,)).  ``workspace``: optional (N, elems) MPS
     scratch to avoid the library's internal allocation."""
@@ -245,9 +286,10 @@ def classify_device(images_dev: torch.Tensor, clf: DeviceClassifier, D: int | No
     else:
         ov, am = out
     with torch.cuda.device(dev):
+        clf.cache_on_stream(_stream_ptr())
         check(lib.oc_encode_classify(
             images_dev.data_ptr(), _in_dtype(images_dev), N, n_pix, _ld(images_dev), L,
-            0 if D is None else int(D), _OC_DT[clf.dtype], _lib.OC_TRUNC_INLINE,
+            0 if D is None else int(D), _OC_DT[clf.dtype], _trunc(trunc),
             clf.packed.data_ptr(), clf._bonds_c, clf._s_c,
             workspace.data_ptr() if workspace is not None else None,
             ov.data_ptr(), am.data_ptr(), _stream_ptr()))
@@ -259,11 +301,12 @@ class HostPipeline:
     into chunks; the pinned-host -> device copy of chunk k+1 runs on a copy
     stream while the kernels of chunk k run on the compute stream, and the
     results return to pinned host buffers asynchronously.  Device staging is
-    allocated once and reused across calls."""
+    allocated once and reused across calls.  (The same schedule inside the
+    library, behind the C ABI: ``classify_host`` / ``oc_classify_host``.)"""
 
     def __init__(self, clf: DeviceClassifier, n_pix: int, D: int | None, chunk: int = 17_500,
-                 in_dtype=torch.float32):
-        self.clf, self.D, self.chunk, self.n_pix = clf, D, int(chunk), n_pix
+                 in_dtype=torch.float32, trunc: str | None = None):
+        self.clf, self.D, self.chunk, self.n_pix, self.trunc = clf, D, int(chunk), n_pix, trunc
         dev = clf.device
         self.dev = dev
         L = n_sites_for(n_pix)
@@ -291,15 +334,68 @@ class HostPipeline:
                 self.copied[b].record(self.copy_stream)
             comp.wait_event(self.copied[b])
             classify_device(self.stage[b][: hi - lo], self.clf, self.D, workspace=self.ws,
-                            out=(self.ov[b][: hi - lo], self.am[b][: hi - lo]))
+                            out=(self.ov[b][: hi - lo], self.am[b][: hi - lo]), trunc=self.trunc)
             self.freed[b].record(comp)
             ov_host[lo:hi].copy_(self.ov[b][: hi - lo], non_blocking=True)
             am_host[lo:hi].copy_(self.am[b][: hi - lo], non_blocking=True)
         comp.synchronize()
 
 
+def _host_array(x):
+    """numpy view of a host tensor / array with unit inner stride (no copy when possible)."""
+    if isinstance(x, torch.Tensor):
+        if x.device.type != "cpu":
+            raise ValueError("classify_host takes HOST images")
+        x = x.numpy()
+    x = np.asarray(x)
+    if x.ndim == 1:
+        x = x[None]
+    if x.ndim != 2:
+        raise ValueError("images must be (N, n_pix)")
+    if x.dtype not in (np.float32, np.float64, np.uint8):
+        x = x.astype(np.float64)
+    if x.strides[1] != x.itemsize or (x.shape[0] > 1 and x.strides[0] % x.itemsize):
+        x = np.ascontiguousarray(x)
+    return x
+
+
+_NP_IN = {np.dtype(np.float32): OC_F32, np.dtype(np.float64): OC_F64, np.dtype(np.uint8): OC_U8}
+
+
+def classify_host(images_host, classifier, D_encode: int | None = 32, dtype: str = "f32", out=None,
+                  trunc: str | None = None, device=None):
+    """HOST buffers in, HOST buffers out through ONE C-ABI call (``oc_classify_host``):
+    the library pipelines host->device copies, kernels and the result copies itself.
+
+    images_host: (N, n_pix) numpy array or CPU tensor, float32 / float64 / uint8 (MNIST's
+    own type; /255 happens in the encoder's load).  Pinned memory overlaps the copies.
+    ``out``: optional (overlaps (N, S), argmax (N,) int32) host arrays/tensors to fill.
+    Returns (overlaps, argmax) as numpy arrays of the compute dtype / int32."""
+    dev = _device(device)
+    clf = _as_classifier(classifier, dtype, dev)
+    x = _host_array(images_host)
+    N, n_pix = x.shape
+    L = n_sites_for(n_pix)
+    if out is None:
+        ov = np.empty((N, clf.S), dtype=_NP_DT[dtype])
+        am = np.empty((N,), dtype=np.int32)
+    else:
+        ov, am = (o.numpy() if isinstance(o, torch.Tensor) else o for o in out)
+        if ov.shape != (N, clf.S) or ov.dtype != _NP_DT[dtype] or not ov.flags.c_contiguous:
+            raise ValueError("out[0] must be a C-contiguous (N, S) array of the compute dtype")
+        if am.shape != (N,) or am.dtype != np.int32 or not am.flags.c_contiguous:
+            raise ValueError("out[1] must be a C-contiguous (N,) int32 array")
+    ld = x.strides[0] // x.itemsize if N > 1 else n_pix
+    with torch.cuda.device(dev):
+        check(lib.oc_classify_host(
+            x.ctypes.data, _NP_IN[x.dtype], N, n_pix, ld, L, 0 if D_encode is None else int(D_encode),
+            _OC_DT[dtype], _trunc(trunc), clf.packed_host.ctypes.data, clf.packed_host.size,
+            clf._bonds_c, clf._s_c, ov.ctypes.data, am.ctypes.data, _stream_ptr()))
+    return ov, am
+
+
 def label_overlaps(images_or_mps, classifier, D_encode: int | None = 32, dtype: str = "f32",
-                   device=None) -> np.ndarray:
+                   device=None, trunc: str | None = None) -> np.ndarray:
     """The reference's inline prediction expression, batched:
     ``[np.abs((mps.H.squeeze() @ classifier.squeeze()).data) for mps in ...]``
     (experiments.py:332-337) -> (N, 16) float64 host array."""
@@ -310,15 +406,16 @@ def label_overlaps(images_or_mps, classifier, D_encode: int | None = 32, dtype: 
     else:
         t = to_device_images(images_or_mps, device)
         clf = _as_classifier(classifier, dtype, t.device)
-        ov, _ = classify_device(t, clf, D_encode)
+        ov, _ = classify_device(t, clf, D_encode, trunc=trunc)
     return ov.double().cpu().numpy()
 
 
-def classify(images, classifier, D_encode: int | None = 32, dtype: str = "f32", device=None):
+def classify(images, classifier, D_encode: int | None = 32, dtype: str = "f32", device=None,
+             trunc: str | None = None):
     """Host in, host out: (overlaps (N, S) float64, argmax (N,) int32)."""
     t = to_device_images(images, device)
     clf = _as_classifier(classifier, dtype, t.device)
-    ov, am = classify_device(t, clf, D_encode)
+    ov, am = classify_device(t, clf, D_encode, trunc=trunc)
     return ov.double().cpu().numpy(), am.cpu().numpy()
 
 
@@ -335,12 +432,12 @@ def count_correct(argmax_dev: torch.Tensor, labels_dev: torch.Tensor) -> torch.T
 
 
 def evaluate(images, labels, classifier, D_encode: int | None = 32, dtype: str = "f32",
-             device=None, all_reduce: bool = True) -> float:
+             device=None, all_reduce: bool = True, trunc: str | None = None) -> float:
     """Top-1 accuracy of this rank's shard, summed over ranks with one
     all-reduce of two int64 when torch.distributed is initialised."""
     t = to_device_images(images, device)
     clf = _as_classifier(classifier, dtype, t.device)
-    _, am = classify_device(t, clf, D_encode)
+    _, am = classify_device(t, clf, D_encode, trunc=trunc)
     lab = torch.as_tensor(np.asarray(labels), dtype=torch.uint8).to(t.device)
     counts = count_correct(am, lab)
     if all_reduce:

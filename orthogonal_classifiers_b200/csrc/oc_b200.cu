@@ -1,6 +1,13 @@
 // C ABI of the B200-native encode + classify path (include/oc_b200.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared
 //        -Xcompiler -fPIC -I include -o liboc_b200.so oc_b200.cu
+//
+// Library state: everything a call needs besides its arguments (Psi workspaces, the re-laid
+// classifier, staging buffers of the host-buffer call, the auxiliary streams) lives in a CONTEXT
+// keyed by (device, stream).  Two calls on different streams or devices never share scratch; two
+// host threads calling on the SAME stream are serialised by the context's mutex.  Scratch of the
+// device-pointer entry points is allocated and freed stream-ordered (cudaMallocAsync /
+// cudaFreeAsync on the call's stream): growing it never synchronises the device.
 #include "oc_b200.h"
 
 #include <cuda_runtime.h>
@@ -10,14 +17,18 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "oc_generic.cuh"
 #include "oc_encode_fast.cuh"
 #include "oc_encode_hw.cuh"
 #include "oc_encode_gram.cuh"
 #include "oc_overlap_fast.cuh"
+#include "oc_sweep.cuh"
 
 namespace {
 
@@ -47,34 +58,116 @@ int clampD(int L, int D) {
 }
 
 int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[oc::kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int i = (dev >= 0 && dev < oc::kMaxDevices) ? dev : 0;
+  if (!sms[i]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms[i] = v > 0 ? v : 148;
   }
-  return sms;
+  return sms[i];
 }
 
-// grow-only device scratch (one process per GPU; guarded for safety)
+// grow-only device scratch owned by one context
 struct Scratch {
   void* p = nullptr;
   size_t cap = 0;
-  int ensure(size_t bytes) {
+  bool async = true;
+  // stream-ordered: earlier work on `st` that uses the old buffer is ordered before its release
+  int ensure(size_t bytes, cudaStream_t st) {
     if (bytes <= cap) return OC_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) return fail(OC_E_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    cap = bytes;
+    release(st);
+    const size_t want = bytes + bytes / 8;  // a little slack: growing call sizes do not reallocate each time
+    cudaError_t e = async ? cudaMallocAsync(&p, want, st) : cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // clear the sticky error of the failed allocation
+      p = nullptr;
+      return fail(OC_E_CUDA, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
     return OC_OK;
   }
+  void release(cudaStream_t st) {
+    if (p) {
+      if (async) cudaFreeAsync(p, st);
+      else cudaFree(p);
+    }
+    p = nullptr;
+    cap = 0;
+  }
 };
-std::mutex g_mu, g_ws_mu;
-Scratch g_mps, g_img, g_clf, g_ov, g_am, g_enc_ws, g_ov_ws;
+
+struct ClfEntry {  // a re-laid classifier the caller declared immutable (oc_classifier_cache)
+  const void* clf = nullptr;
+  uint64_t key = 0;  // shapes + options the layout depends on; 0 = not prepared yet
+  Scratch prepared;
+};
+
+struct HostPipe {  // oc_classify_host: double-buffered H2D | kernels | D2H
+  cudaStream_t copy = nullptr, back = nullptr;
+  cudaEvent_t copied[2] = {}, freed[2] = {}, done[2] = {}, backdone[2] = {};
+  Scratch stage[2], ov[2], am[2], clf, mps;
+  HostPipe() {
+    for (int b = 0; b < 2; ++b) stage[b].async = ov[b].async = am[b].async = false;
+    clf.async = mps.async = false;
+  }
+};
+
+struct Ctx {
+  std::mutex mu;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Scratch mps, enc_ws, ov_ws, sw_img, sw_mps, sw_sv, sw_sw;
+  oc::SplitStreams split;
+  std::vector<ClfEntry> cache;
+  HostPipe hp;
+};
+
+std::mutex g_ctx_mu;
+std::map<std::pair<int, void*>, std::unique_ptr<Ctx>> g_ctx;
 int g_force_generic = 0;
+int g_host_chunk = 0;  // 0 = default per input type
+
+Ctx& get_ctx(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto& slot = g_ctx[{dev, (void*)st}];
+  if (!slot) {
+    slot.reset(new Ctx);
+    slot->device = dev;
+    slot->stream = st;
+  }
+  return *slot;
+}
+
+void release_ctx(Ctx& cx) {
+  cudaStream_t st = cx.stream;
+  for (Scratch* s : {&cx.mps, &cx.enc_ws, &cx.ov_ws, &cx.sw_img, &cx.sw_mps, &cx.sw_sv, &cx.sw_sw}) s->release(st);
+  for (auto& e : cx.cache) e.prepared.release(st);
+  cx.cache.clear();
+  HostPipe& hp = cx.hp;
+  for (int b = 0; b < 2; ++b) {
+    hp.stage[b].release(st);
+    hp.ov[b].release(st);
+    hp.am[b].release(st);
+    for (cudaEvent_t* ev : {&hp.copied[b], &hp.freed[b], &hp.done[b], &hp.backdone[b]}) {
+      if (*ev) cudaEventDestroy(*ev);
+      *ev = nullptr;
+    }
+  }
+  hp.clf.release(st);
+  hp.mps.release(st);
+  if (hp.copy) cudaStreamDestroy(hp.copy);
+  if (hp.back) cudaStreamDestroy(hp.back);
+  hp.copy = hp.back = nullptr;
+  if (cx.split.aux) cudaStreamDestroy(cx.split.aux);
+  if (cx.split.fork) cudaEventDestroy(cx.split.fork);
+  if (cx.split.join) cudaEventDestroy(cx.split.join);
+  cx.split = oc::SplitStreams{};
+}
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
@@ -85,17 +178,282 @@ int set_smem(K kernel, size_t bytes) {
   return OC_OK;
 }
 
+int mps_layout(int L, int D, int32_t* bonds, int64_t* site_offsets) {
+  if (L < 1 || L > OC_MAX_L) return fail(OC_E_ARG, "L=%d outside [1,%d]", L, OC_MAX_L);
+  D = clampD(L, D);
+  int64_t off = 0;
+  int b[OC_MAX_L + 1];
+  for (int n = 0; n <= L; ++n) b[n] = std::min(std::min(1 << n, 1 << (L - n)), D);
+  for (int n = 0; n <= L; ++n) {
+    if (bonds) bonds[n] = b[n];
+    if (site_offsets) site_offsets[n] = off;
+    if (n < L) off += 2LL * b[n] * b[n + 1];
+  }
+  return OC_OK;
+}
+
+int svals_width(int L, int D) {
+  if (L < 1 || L > OC_MAX_L) return -1;
+  D = clampD(L, D);
+  int w = 1;
+  for (int n = 0; n < L; ++n) {
+    int bn = std::min(std::min(1 << n, 1 << (L - n)), D);
+    w = std::max(w, std::min(2 * bn, 1 << (L - n - 1)));
+  }
+  return w;
+}
+
+int check_encode_args(const void* images, const void* out, int in_dtype, int64_t N, int n_pix, int64_t ld, int L,
+                      int dtype, int trunc_mode) {
+  if (N < 0) return fail(OC_E_ARG, "N=%lld < 0", (long long)N);
+  if (L < 1 || L > OC_MAX_L) return fail(OC_E_ARG, "L=%d outside [1,%d] (n_pix <= 1024)", L, OC_MAX_L);
+  if (n_pix < 1 || n_pix > (1 << L)) return fail(OC_E_ARG, "n_pix=%d does not fit 2^L=%d", n_pix, 1 << L);
+  if (n_pix > 1 && n_pix <= (1 << (L - 1)))
+    return fail(OC_E_ARG, "L=%d is not ceil(log2(n_pix=%d)) (tools.py:218)", L, n_pix);
+  if (ld < n_pix) return fail(OC_E_ARG, "ld=%lld < n_pix=%d", (long long)ld, n_pix);
+  if (in_dtype != OC_F32 && in_dtype != OC_F64 && in_dtype != OC_U8) return fail(OC_E_ARG, "bad in_dtype %d", in_dtype);
+  if (dtype != OC_F32 && dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", dtype);
+  if (trunc_mode != OC_TRUNC_INLINE && trunc_mode != OC_TRUNC_SWEEP)
+    return fail(OC_E_ARG, "unsupported trunc_mode %d", trunc_mode);
+  if (N > 0 && (!images || !out)) return fail(OC_E_ARG, "null images/output pointer");
+  return OC_OK;
+}
+
+// ---- inline-truncating encoder (also the exact one when D does not truncate) ----
+int encode_inline(Ctx& cx, const void* images_dev, int in_dtype, int64_t N, int n_pix, int64_t ld, int L, int D,
+                  int dtype, void* mps_out_dev, void* svals_out_dev, int32_t* sweeps_out_dev, cudaStream_t st) {
+  oc::EncodeParams P;
+  memset(&P, 0, sizeof(P));
+  P.images = images_dev;
+  P.in_dtype = in_dtype;
+  P.N = N;
+  P.n_pix = n_pix;
+  P.ld = ld;
+  P.L = L;
+  P.D = clampD(L, D);
+  P.mps_out = mps_out_dev;
+  P.svals_out = svals_out_dev;
+  P.sweeps_out = sweeps_out_dev;
+  mps_layout(L, P.D, P.bonds, P.site_off);
+  P.mps_stride = P.site_off[L];
+  P.sv_width = svals_width(L, P.D);
+
+  // specialised path: fp32, L = 10 (register-resident Jacobi chain)
+  if (dtype == OC_F32 && !g_force_generic && oc::encode_fast_supported(P)) {
+    // Psi ping-pong workspace of the step-major chain (grow-only, owned by the context)
+    const int64_t chunk = std::min<int64_t>(N, oc::kEncodeChunk);
+    if (int rc = cx.enc_ws.ensure((size_t)2 * chunk * oc::kWsStride * sizeof(float) + 2 * oc::encode_sort_bytes(chunk) + 512, st))
+      return rc;
+    int rc = oc::encode_fast_launch(P, reinterpret_cast<float*>(cx.enc_ws.p), num_sms(), st, &cx.split);
+    if (rc == 0) return OC_OK;
+    if (rc > 0) return fail(OC_E_CUDA, "encode_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  }
+
+  const int warps = 4;
+  const size_t esz = dtype == OC_F32 ? 4 : 8;
+  const size_t smem = (size_t)warps * (3 * (1 << L) + 64) * esz;
+  const int64_t blocks_needed = (N + warps - 1) / warps;
+  const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)num_sms() * 16);
+  if (dtype == OC_F32) {
+    if (int rc = set_smem(oc::encode_generic_kernel<float>, smem)) return rc;
+    oc::encode_generic_kernel<float><<<grid, warps * 32, smem, st>>>(P);
+  } else {
+    if (int rc = set_smem(oc::encode_generic_kernel<double>, smem)) return rc;
+    oc::encode_generic_kernel<double><<<grid, warps * 32, smem, st>>>(P);
+  }
+  OC_CUDA(cudaGetLastError());
+  return OC_OK;
+}
+
+// ---- OC_TRUNC_SWEEP (oc_sweep.cuh): bit reversal | inline chain | QR pass back to the left gauge ----
+constexpr int64_t kSweepChunk = 32768;
+
+template <typename T>
+int encode_sweep_t(Ctx& cx, const void* images_dev, int in_dtype, int64_t N, int n_pix, int64_t ld, int L, int D,
+                   int dtype, void* mps_out_dev, void* svals_out_dev, int32_t* sweeps_out_dev, cudaStream_t st) {
+  oc::sweep::SweepParams S;
+  memset(&S, 0, sizeof(S));
+  const int Dc = clampD(L, D);
+  mps_layout(L, Dc, S.bonds, S.site_off);
+  S.mps_stride = S.site_off[L];
+  S.sv_width = svals_width(L, Dc);
+  S.L = L;
+  const int64_t chunk = std::min<int64_t>(N, kSweepChunk);
+  const int cap = 1 << L;
+  const size_t in_esz = in_dtype == OC_F32 ? 4 : (in_dtype == OC_F64 ? 8 : 1);
+  if (int rc = cx.sw_img.ensure((size_t)chunk * cap * sizeof(T), st)) return rc;
+  if (int rc = cx.sw_mps.ensure((size_t)chunk * S.mps_stride * sizeof(T), st)) return rc;
+  if (svals_out_dev)
+    if (int rc = cx.sw_sv.ensure((size_t)chunk * L * S.sv_width * sizeof(T), st)) return rc;
+  if (sweeps_out_dev)
+    if (int rc = cx.sw_sw.ensure((size_t)chunk * L * sizeof(int32_t), st)) return rc;
+  const int warps = sizeof(T) == 8 ? 2 : 4;
+  const size_t smem = (size_t)warps * oc::sweep::kSwPerWarp * sizeof(T);
+  if (int rc = set_smem(oc::sweep::sweep_back_kernel<T>, smem)) return rc;
+  for (int64_t lo = 0; lo < N; lo += kSweepChunk) {
+    const int64_t n = std::min<int64_t>(kSweepChunk, N - lo);
+    const char* src = reinterpret_cast<const char*>(images_dev) + (size_t)lo * ld * in_esz;
+    T* rimg = reinterpret_cast<T*>(cx.sw_img.p);
+    oc::sweep::bitrev_kernel<T><<<(int)std::min<int64_t>(n, (int64_t)num_sms() * 8), 256, 0, st>>>(src, in_dtype, n,
+                                                                                                  n_pix, ld, L, rimg);
+    OC_CUDA(cudaGetLastError());
+    if (int rc = encode_inline(cx, rimg, dtype, n, cap, cap, L, D, dtype, cx.sw_mps.p,
+                               svals_out_dev ? cx.sw_sv.p : nullptr,
+                               sweeps_out_dev ? reinterpret_cast<int32_t*>(cx.sw_sw.p) : nullptr, st))
+      return rc;
+    S.tmp_mps = cx.sw_mps.p;
+    S.mps_out = reinterpret_cast<T*>(mps_out_dev) + (size_t)lo * S.mps_stride;
+    S.tmp_sv = svals_out_dev ? cx.sw_sv.p : nullptr;
+    S.sv_out = svals_out_dev ? reinterpret_cast<T*>(svals_out_dev) + (size_t)lo * L * S.sv_width : nullptr;
+    S.tmp_sw = sweeps_out_dev ? reinterpret_cast<const int32_t*>(cx.sw_sw.p) : nullptr;
+    S.sw_out = sweeps_out_dev ? sweeps_out_dev + (size_t)lo * L : nullptr;
+    S.N = n;
+    const int64_t need = (n + warps - 1) / warps;
+    const int grid = (int)std::min<int64_t>(need, (int64_t)num_sms() * 16);
+    oc::sweep::sweep_back_kernel<T><<<grid, warps * 32, smem, st>>>(S);
+    OC_CUDA(cudaGetLastError());
+  }
+  return OC_OK;
+}
+
+int encode_impl(Ctx& cx, const void* images_dev, int in_dtype, int64_t N, int n_pix, int64_t ld, int L, int D,
+                int dtype, int trunc_mode, void* mps_out_dev, void* svals_out_dev, int32_t* sweeps_out_dev,
+                cudaStream_t st) {
+  if (int rc = check_encode_args(images_dev, mps_out_dev, in_dtype, N, n_pix, ld, L, dtype, trunc_mode)) return rc;
+  if (N == 0) return OC_OK;
+  // a D that truncates no bond (D >= 2^floor(L/2)): every variant is the exact chain
+  const bool truncates = clampD(L, D) < (1 << (L / 2));
+  if (trunc_mode == OC_TRUNC_SWEEP && truncates) {
+    if (dtype == OC_F32)
+      return encode_sweep_t<float>(cx, images_dev, in_dtype, N, n_pix, ld, L, D, dtype, mps_out_dev, svals_out_dev,
+                                   sweeps_out_dev, st);
+    return encode_sweep_t<double>(cx, images_dev, in_dtype, N, n_pix, ld, L, D, dtype, mps_out_dev, svals_out_dev,
+                                  sweeps_out_dev, st);
+  }
+  return encode_inline(cx, images_dev, in_dtype, N, n_pix, ld, L, D, dtype, mps_out_dev, svals_out_dev,
+                       sweeps_out_dev, st);
+}
+
+uint64_t fnv(uint64_t h, const void* p, size_t n) {
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(p);
+  for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+
+int overlap_impl(Ctx& cx, const void* mps_dev, const int32_t* mps_bonds_host, const void* clf_dev,
+                 const int32_t* clf_bonds_host, const int32_t* clf_s_host, int L, int64_t N, int dtype,
+                 void* overlaps_out_dev, int32_t* argmax_out_dev, cudaStream_t st) {
+  if (N < 0) return fail(OC_E_ARG, "N=%lld < 0", (long long)N);
+  if (L < 1 || L > OC_MAX_SITES) return fail(OC_E_ARG, "L=%d outside [1,%d]", L, OC_MAX_SITES);
+  if (dtype != OC_F32 && dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", dtype);
+  if (N == 0) return OC_OK;
+  if (!mps_dev || !clf_dev || !overlaps_out_dev || !mps_bonds_host || !clf_bonds_host || !clf_s_host)
+    return fail(OC_E_ARG, "null pointer argument");
+
+  oc::OverlapParams P;
+  memset(&P, 0, sizeof(P));
+  P.mps = mps_dev;
+  P.clf = clf_dev;
+  P.N = N;
+  P.L = L;
+  P.c = -1;
+  P.S = 1;
+  for (int n = 0; n < L; ++n) {
+    if (clf_s_host[n] < 1) return fail(OC_E_ARG, "s[%d]=%d < 1", n, clf_s_host[n]);
+    if (clf_s_host[n] > 1) {
+      if (P.c >= 0) return fail(OC_E_ARG, "more than one site carries a label leg (sites %d and %d)", P.c, n);
+      P.c = n;
+      P.S = clf_s_host[n];
+    }
+  }
+  if (P.c < 0) P.c = L - 1;  // no label leg at all: scalar overlap, treat last site as hairy with S = 1
+  if (P.S > OC_MAX_LABEL) return fail(OC_E_ARG, "label leg %d > %d", P.S, OC_MAX_LABEL);
+  if (mps_bonds_host[0] != 1 || mps_bonds_host[L] != 1 || clf_bonds_host[0] != 1 || clf_bonds_host[L] != 1)
+    return fail(OC_E_ARG, "edge bonds must be 1");
+  int64_t mo = 0, co = 0;
+  for (int n = 0; n <= L; ++n) {
+    P.a[n] = mps_bonds_host[n];
+    P.B[n] = clf_bonds_host[n];
+    if (P.a[n] < 1 || P.B[n] < 1) return fail(OC_E_ARG, "bond %d < 1", n);
+    P.amax = std::max(P.amax, P.a[n]);
+    P.Bmax = std::max(P.Bmax, P.B[n]);
+    P.mps_off[n] = mo;
+    P.clf_off[n] = co;
+    if (n < L) {
+      mo += 2LL * mps_bonds_host[n] * mps_bonds_host[n + 1];
+      co += 2LL * clf_s_host[n] * clf_bonds_host[n] * clf_bonds_host[n + 1];
+    }
+  }
+  P.mps_stride = mo;
+  P.overlaps = overlaps_out_dev;
+  P.argmax = argmax_out_dev;
+
+  if (dtype == OC_F32 && !g_force_generic && oc::overlap_fast_supported(P)) {
+    const size_t bytes = oc::overlap_fast_scratch_floats(P) * sizeof(float);
+    float* ws = nullptr;
+    bool do_prep = true;
+    for (auto& e : cx.cache) {
+      if (e.clf != clf_dev) continue;
+      // the re-laid classifier depends on its shapes, on the image bond profile (which kernel
+      // variant runs) and on the option switches
+      uint64_t key = 1469598103934665603ull;
+      key = fnv(key, &P.L, sizeof(P.L));
+      key = fnv(key, &P.c, sizeof(P.c));
+      key = fnv(key, &P.S, sizeof(P.S));
+      key = fnv(key, P.a, sizeof(int) * (L + 1));
+      key = fnv(key, P.B, sizeof(int) * (L + 1));
+      const int opts[3] = {oc::overlap_static_shapes(), oc::overlap_mma(), oc::overlap_pad()};
+      key = fnv(key, opts, sizeof(opts));
+      key |= 1ull;
+      if (int rc = e.prepared.ensure(bytes, st)) return rc;
+      ws = reinterpret_cast<float*>(e.prepared.p);
+      do_prep = e.key != key;
+      e.key = key;
+      break;
+    }
+    if (!ws) {
+      if (int rc = cx.ov_ws.ensure(bytes, st)) return rc;
+      ws = reinterpret_cast<float*>(cx.ov_ws.p);
+    }
+    int rc = oc::overlap_fast_launch(P, ws, num_sms(), st, do_prep);
+    if (rc == 0) return OC_OK;
+    if (rc > 0) return fail(OC_E_CUDA, "overlap_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  }
+
+  const size_t esz = dtype == OC_F32 ? 4 : 8;
+  const size_t per_warp = ((size_t)5 * P.amax * P.Bmax + 64) * esz;
+  int warps = 4;
+  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+  const size_t smem = per_warp * warps;
+  if (smem > 227 * 1024) return fail(OC_E_ARG, "bonds too large for shared memory (a=%d, B=%d)", P.amax, P.Bmax);
+  const int64_t blocks_needed = (N + warps - 1) / warps;
+  const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)num_sms() * 16);
+  if (dtype == OC_F32) {
+    if (int rc = set_smem(oc::overlap_generic_kernel<float>, smem)) return rc;
+    oc::overlap_generic_kernel<float><<<grid, warps * 32, smem, st>>>(P);
+  } else {
+    if (int rc = set_smem(oc::overlap_generic_kernel<double>, smem)) return rc;
+    oc::overlap_generic_kernel<double><<<grid, warps * 32, smem, st>>>(P);
+  }
+  OC_CUDA(cudaGetLastError());
+  return OC_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-int oc_version(void) { return 100; }
+int oc_version(void) { return 200; }
 
 const char* oc_last_error(void) { return g_err.c_str(); }
 
 int oc_set_option(const char* key, int value) {
   if (key && !strcmp(key, "force_generic")) {
     g_force_generic = value;
+    return OC_OK;
+  }
+  if (key && !strcmp(key, "host_chunk") && value >= 0) {
+    g_host_chunk = value;
     return OC_OK;
   }
   if (key && !strcmp(key, "enc_events")) {
@@ -154,172 +512,28 @@ int oc_set_option(const char* key, int value) {
   return fail(OC_E_ARG, "unknown option %s", key ? key : "(null)");
 }
 
-int oc_mps_layout(int L, int D, int32_t* bonds, int64_t* site_offsets) {
-  if (L < 1 || L > OC_MAX_L) return fail(OC_E_ARG, "L=%d outside [1,%d]", L, OC_MAX_L);
-  D = clampD(L, D);
-  int64_t off = 0;
-  int b[OC_MAX_L + 1];
-  for (int n = 0; n <= L; ++n) b[n] = std::min(std::min(1 << n, 1 << (L - n)), D);
-  for (int n = 0; n <= L; ++n) {
-    if (bonds) bonds[n] = b[n];
-    if (site_offsets) site_offsets[n] = off;
-    if (n < L) off += 2LL * b[n] * b[n + 1];
-  }
-  return OC_OK;
-}
+int oc_mps_layout(int L, int D, int32_t* bonds, int64_t* site_offsets) { return mps_layout(L, D, bonds, site_offsets); }
 
-int oc_svals_width(int L, int D) {
-  if (L < 1 || L > OC_MAX_L) return -1;
-  D = clampD(L, D);
-  int w = 1;
-  for (int n = 0; n < L; ++n) {
-    int bn = std::min(std::min(1 << n, 1 << (L - n)), D);
-    w = std::max(w, std::min(2 * bn, 1 << (L - n - 1)));
-  }
-  return w;
-}
+int oc_svals_width(int L, int D) { return svals_width(L, D); }
 
 int oc_encode_batch(const void* images_dev, int in_dtype, int64_t N, int n_pix, int64_t ld,
                     int L, int D, int dtype, int trunc_mode, void* mps_out_dev,
                     void* svals_out_dev, int32_t* sweeps_out_dev, void* stream) {
-  if (N < 0) return fail(OC_E_ARG, "N=%lld < 0", (long long)N);
-  if (N == 0) return OC_OK;
-  if (!images_dev || !mps_out_dev) return fail(OC_E_ARG, "null images/mps pointer");
-  if (L < 1 || L > OC_MAX_L) return fail(OC_E_ARG, "L=%d outside [1,%d] (n_pix <= 1024)", L, OC_MAX_L);
-  if (n_pix < 1 || n_pix > (1 << L)) return fail(OC_E_ARG, "n_pix=%d does not fit 2^L=%d", n_pix, 1 << L);
-  if (n_pix > 1 && n_pix <= (1 << (L - 1)))
-    return fail(OC_E_ARG, "L=%d is not ceil(log2(n_pix=%d)) (tools.py:218)", L, n_pix);
-  if (ld < n_pix) return fail(OC_E_ARG, "ld=%lld < n_pix=%d", (long long)ld, n_pix);
-  if (in_dtype != OC_F32 && in_dtype != OC_F64 && in_dtype != OC_U8) return fail(OC_E_ARG, "bad in_dtype %d", in_dtype);
-  if (dtype != OC_F32 && dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", dtype);
-  if (trunc_mode != OC_TRUNC_INLINE) return fail(OC_E_ARG, "unsupported trunc_mode %d", trunc_mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-
-  oc::EncodeParams P;
-  memset(&P, 0, sizeof(P));
-  P.images = images_dev;
-  P.in_dtype = in_dtype;
-  P.N = N;
-  P.n_pix = n_pix;
-  P.ld = ld;
-  P.L = L;
-  P.D = clampD(L, D);
-  P.mps_out = mps_out_dev;
-  P.svals_out = svals_out_dev;
-  P.sweeps_out = sweeps_out_dev;
-  oc_mps_layout(L, P.D, P.bonds, P.site_off);
-  P.mps_stride = P.site_off[L];
-  P.sv_width = oc_svals_width(L, P.D);
-
-  // specialised path: fp32, L = 10 (register-resident Jacobi chain)
-  if (dtype == OC_F32 && !g_force_generic && oc::encode_fast_supported(P)) {
-    // Psi ping-pong workspace of the step-major chain (grow-only, library-owned)
-    const int64_t chunk = std::min<int64_t>(N, oc::kEncodeChunk);
-    float* ws = nullptr;
-    {
-      std::lock_guard<std::mutex> lk(g_ws_mu);
-      if (int rc = g_enc_ws.ensure((size_t)2 * chunk * oc::kWsStride * sizeof(float) + 2 * oc::encode_sort_bytes(chunk) + 512)) return rc;
-      ws = reinterpret_cast<float*>(g_enc_ws.p);
-    }
-    int rc = oc::encode_fast_launch(P, ws, num_sms(), st);
-    if (rc == 0) return OC_OK;
-    if (rc > 0) return fail(OC_E_CUDA, "encode_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-  }
-
-  const int warps = 4;
-  const size_t esz = dtype == OC_F32 ? 4 : 8;
-  const size_t smem = (size_t)warps * (3 * (1 << L) + 64) * esz;
-  const int64_t blocks_needed = (N + warps - 1) / warps;
-  const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)num_sms() * 16);
-  if (dtype == OC_F32) {
-    if (int rc = set_smem(oc::encode_generic_kernel<float>, smem)) return rc;
-    oc::encode_generic_kernel<float><<<grid, warps * 32, smem, st>>>(P);
-  } else {
-    if (int rc = set_smem(oc::encode_generic_kernel<double>, smem)) return rc;
-    oc::encode_generic_kernel<double><<<grid, warps * 32, smem, st>>>(P);
-  }
-  OC_CUDA(cudaGetLastError());
-  return OC_OK;
+  Ctx& cx = get_ctx(st);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  return encode_impl(cx, images_dev, in_dtype, N, n_pix, ld, L, D, dtype, trunc_mode, mps_out_dev, svals_out_dev,
+                     sweeps_out_dev, st);
 }
 
 int oc_overlap_batch(const void* mps_dev, const int32_t* mps_bonds_host, const void* clf_dev,
                      const int32_t* clf_bonds_host, const int32_t* clf_s_host, int L, int64_t N,
                      int dtype, void* overlaps_out_dev, int32_t* argmax_out_dev, void* stream) {
-  if (N < 0) return fail(OC_E_ARG, "N=%lld < 0", (long long)N);
-  if (N == 0) return OC_OK;
-  if (!mps_dev || !clf_dev || !overlaps_out_dev || !mps_bonds_host || !clf_bonds_host || !clf_s_host)
-    return fail(OC_E_ARG, "null pointer argument");
-  if (L < 1 || L > OC_MAX_SITES) return fail(OC_E_ARG, "L=%d outside [1,%d]", L, OC_MAX_SITES);
-  if (dtype != OC_F32 && dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", dtype);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-
-  oc::OverlapParams P;
-  memset(&P, 0, sizeof(P));
-  P.mps = mps_dev;
-  P.clf = clf_dev;
-  P.N = N;
-  P.L = L;
-  P.c = -1;
-  P.S = 1;
-  for (int n = 0; n < L; ++n) {
-    if (clf_s_host[n] < 1) return fail(OC_E_ARG, "s[%d]=%d < 1", n, clf_s_host[n]);
-    if (clf_s_host[n] > 1) {
-      if (P.c >= 0) return fail(OC_E_ARG, "more than one site carries a label leg (sites %d and %d)", P.c, n);
-      P.c = n;
-      P.S = clf_s_host[n];
-    }
-  }
-  if (P.c < 0) P.c = L - 1;  // no label leg at all: scalar overlap, treat last site as hairy with S = 1
-  if (P.S > OC_MAX_LABEL) return fail(OC_E_ARG, "label leg %d > %d", P.S, OC_MAX_LABEL);
-  if (mps_bonds_host[0] != 1 || mps_bonds_host[L] != 1 || clf_bonds_host[0] != 1 || clf_bonds_host[L] != 1)
-    return fail(OC_E_ARG, "edge bonds must be 1");
-  int64_t mo = 0, co = 0;
-  for (int n = 0; n <= L; ++n) {
-    P.a[n] = mps_bonds_host[n];
-    P.B[n] = clf_bonds_host[n];
-    if (P.a[n] < 1 || P.B[n] < 1) return fail(OC_E_ARG, "bond %d < 1", n);
-    P.amax = std::max(P.amax, P.a[n]);
-    P.Bmax = std::max(P.Bmax, P.B[n]);
-    P.mps_off[n] = mo;
-    P.clf_off[n] = co;
-    if (n < L) {
-      mo += 2LL * mps_bonds_host[n] * mps_bonds_host[n + 1];
-      co += 2LL * clf_s_host[n] * clf_bonds_host[n] * clf_bonds_host[n + 1];
-    }
-  }
-  P.mps_stride = mo;
-  P.overlaps = overlaps_out_dev;
-  P.argmax = argmax_out_dev;
-
-  if (dtype == OC_F32 && !g_force_generic && oc::overlap_fast_supported(P)) {
-    float* ws = nullptr;
-    {
-      std::lock_guard<std::mutex> lk(g_ws_mu);
-      if (int rc = g_ov_ws.ensure(oc::overlap_fast_scratch_floats(P) * sizeof(float))) return rc;
-      ws = reinterpret_cast<float*>(g_ov_ws.p);
-    }
-    int rc = oc::overlap_fast_launch(P, ws, num_sms(), st);
-    if (rc == 0) return OC_OK;
-    if (rc > 0) return fail(OC_E_CUDA, "overlap_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-  }
-
-  const size_t esz = dtype == OC_F32 ? 4 : 8;
-  const size_t per_warp = ((size_t)5 * P.amax * P.Bmax + 64) * esz;
-  int warps = 4;
-  while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-  const size_t smem = per_warp * warps;
-  if (smem > 227 * 1024) return fail(OC_E_ARG, "bonds too large for shared memory (a=%d, B=%d)", P.amax, P.Bmax);
-  const int64_t blocks_needed = (N + warps - 1) / warps;
-  const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)num_sms() * 16);
-  if (dtype == OC_F32) {
-    if (int rc = set_smem(oc::overlap_generic_kernel<float>, smem)) return rc;
-    oc::overlap_generic_kernel<float><<<grid, warps * 32, smem, st>>>(P);
-  } else {
-    if (int rc = set_smem(oc::overlap_generic_kernel<double>, smem)) return rc;
-    oc::overlap_generic_kernel<double><<<grid, warps * 32, smem, st>>>(P);
-  }
-  OC_CUDA(cudaGetLastError());
-  return OC_OK;
+  Ctx& cx = get_ctx(st);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  return overlap_impl(cx, mps_dev, mps_bonds_host, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype,
+                      overlaps_out_dev, argmax_out_dev, st);
 }
 
 int oc_encode_classify(const void* images_dev, int in_dtype, int64_t N, int n_pix, int64_t ld,
@@ -327,22 +541,55 @@ int oc_encode_classify(const void* images_dev, int in_dtype, int64_t N, int n_pi
                        const int32_t* clf_bonds_host, const int32_t* clf_s_host,
                        void* workspace_dev, void* overlaps_out_dev, int32_t* argmax_out_dev,
                        void* stream) {
+  if (int rc = check_encode_args(images_dev, overlaps_out_dev, in_dtype, N, n_pix, ld, L, dtype, trunc_mode)) return rc;
   if (N == 0) return OC_OK;
+  if (!clf_dev || !clf_bonds_host || !clf_s_host) return fail(OC_E_ARG, "null classifier argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Ctx& cx = get_ctx(st);
+  std::lock_guard<std::mutex> lk(cx.mu);
   int32_t bonds[OC_MAX_L + 1];
   int64_t offs[OC_MAX_L + 1];
-  if (int rc = oc_mps_layout(L, D, bonds, offs)) return rc;
+  if (int rc = mps_layout(L, D, bonds, offs)) return rc;
   const size_t esz = dtype == OC_F32 ? 4 : 8;
   void* ws = workspace_dev;
   if (!ws) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (int rc = g_mps.ensure((size_t)N * offs[L] * esz)) return rc;
-    ws = g_mps.p;
+    if (int rc = cx.mps.ensure((size_t)N * offs[L] * esz, st)) return rc;
+    ws = cx.mps.p;
   }
-  if (int rc = oc_encode_batch(images_dev, in_dtype, N, n_pix, ld, L, D, dtype, trunc_mode, ws,
-                               nullptr, nullptr, stream))
+  if (int rc = encode_impl(cx, images_dev, in_dtype, N, n_pix, ld, L, D, dtype, trunc_mode, ws, nullptr, nullptr, st))
     return rc;
-  return oc_overlap_batch(ws, bonds, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype,
-                          overlaps_out_dev, argmax_out_dev, stream);
+  return overlap_impl(cx, ws, bonds, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype, overlaps_out_dev,
+                      argmax_out_dev, st);
+}
+
+int oc_classifier_cache(const void* clf_dev, int enable, void* stream) {
+  if (!clf_dev) return fail(OC_E_ARG, "null classifier pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Ctx& cx = get_ctx(st);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  for (size_t i = 0; i < cx.cache.size(); ++i) {
+    if (cx.cache[i].clf != clf_dev) continue;
+    if (enable) {
+      cx.cache[i].key = 0;  // contents may have changed: re-lay on the next use
+    } else {
+      cx.cache[i].prepared.release(st);
+      cx.cache.erase(cx.cache.begin() + i);
+    }
+    return OC_OK;
+  }
+  if (enable) {
+    cx.cache.emplace_back();
+    cx.cache.back().clf = clf_dev;
+  }
+  return OC_OK;
+}
+
+int oc_release(void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Ctx& cx = get_ctx(st);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  release_ctx(cx);
+  return OC_OK;
 }
 
 int oc_count_correct(const int32_t* argmax_dev, const uint8_t* labels_dev, int64_t N,
@@ -412,35 +659,71 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
                      int D, int dtype, int trunc_mode, const void* clf_packed_host,
                      int64_t clf_elems, const int32_t* clf_bonds_host, const int32_t* clf_s_host,
                      void* overlaps_out_host, int32_t* argmax_out_host, void* stream) {
-  if (N < 0) return fail(OC_E_ARG, "N < 0");
+  if (int rc = check_encode_args(images_host, overlaps_out_host, in_dtype, N, n_pix, ld, L, dtype, trunc_mode)) return rc;
   if (N == 0) return OC_OK;
-  if (!images_host || !clf_packed_host || !overlaps_out_host) return fail(OC_E_ARG, "null pointer argument");
-  if (dtype != OC_F32 && dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", dtype);
+  if (!clf_packed_host || !clf_bonds_host || !clf_s_host || clf_elems < 1) return fail(OC_E_ARG, "null classifier argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t esz = dtype == OC_F32 ? 4 : 8;
   const size_t isz = in_dtype == OC_F32 ? 4 : (in_dtype == OC_F64 ? 8 : 1);
   int S = 1;
   for (int n = 0; n < L; ++n) S = std::max(S, (int)clf_s_host[n]);
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (int rc = g_img.ensure((size_t)N * ld * isz)) return rc;
-  if (int rc = g_clf.ensure((size_t)clf_elems * esz)) return rc;
-  if (int rc = g_ov.ensure((size_t)N * S * esz)) return rc;
-  if (int rc = g_am.ensure((size_t)N * sizeof(int32_t))) return rc;
+  int64_t expect = 0;
+  for (int n = 0; n < L; ++n) expect += 2LL * clf_s_host[n] * clf_bonds_host[n] * clf_bonds_host[n + 1];
+  if (expect != clf_elems) return fail(OC_E_ARG, "clf_elems=%lld does not match the bonds (%lld)", (long long)clf_elems, (long long)expect);
   int32_t bonds[OC_MAX_L + 1];
   int64_t offs[OC_MAX_L + 1];
-  if (int rc = oc_mps_layout(L, D, bonds, offs)) return rc;
-  if (int rc = g_mps.ensure((size_t)N * offs[L] * esz)) return rc;
-  OC_CUDA(cudaMemcpyAsync(g_img.p, images_host, (size_t)N * ld * isz, cudaMemcpyHostToDevice, st));
-  OC_CUDA(cudaMemcpyAsync(g_clf.p, clf_packed_host, (size_t)clf_elems * esz, cudaMemcpyHostToDevice, st));
-  if (int rc = oc_encode_batch(g_img.p, in_dtype, N, n_pix, ld, L, D, dtype, trunc_mode, g_mps.p,
-                               nullptr, nullptr, stream))
-    return rc;
-  if (int rc = oc_overlap_batch(g_mps.p, bonds, g_clf.p, clf_bonds_host, clf_s_host, L, N, dtype,
-                                g_ov.p, reinterpret_cast<int32_t*>(g_am.p), stream))
-    return rc;
-  OC_CUDA(cudaMemcpyAsync(overlaps_out_host, g_ov.p, (size_t)N * S * esz, cudaMemcpyDeviceToHost, st));
-  if (argmax_out_host)
-    OC_CUDA(cudaMemcpyAsync(argmax_out_host, g_am.p, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (int rc = mps_layout(L, D, bonds, offs)) return rc;
+  Ctx& cx = get_ctx(st);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  HostPipe& hp = cx.hp;
+  if (!hp.copy) {
+    OC_CUDA(cudaStreamCreateWithFlags(&hp.copy, cudaStreamNonBlocking));
+    OC_CUDA(cudaStreamCreateWithFlags(&hp.back, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b)
+      for (cudaEvent_t* ev : {&hp.copied[b], &hp.freed[b], &hp.done[b], &hp.backdone[b]})
+        OC_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  }
+  // chunk schedule: the copy of chunk k + 1 runs under the kernels of chunk k.  Defaults measured on
+  // B200; oc_set_option("host_chunk", n) overrides.
+  int64_t chunk = g_host_chunk > 0 ? g_host_chunk : (in_dtype == OC_U8 ? 35000 : 17500);
+  chunk = std::min<int64_t>(chunk, N);
+  for (int b = 0; b < 2; ++b) {
+    if (int rc = hp.stage[b].ensure((size_t)chunk * ld * isz, st)) return rc;
+    if (int rc = hp.ov[b].ensure((size_t)chunk * S * esz, st)) return rc;
+    if (int rc = hp.am[b].ensure((size_t)chunk * sizeof(int32_t), st)) return rc;
+  }
+  if (int rc = hp.clf.ensure((size_t)clf_elems * esz, st)) return rc;
+  if (int rc = hp.mps.ensure((size_t)chunk * offs[L] * esz, st)) return rc;
+  OC_CUDA(cudaMemcpyAsync(hp.clf.p, clf_packed_host, (size_t)clf_elems * esz, cudaMemcpyHostToDevice, st));
+  int k = 0;
+  for (int64_t lo = 0; lo < N; lo += chunk, ++k) {
+    const int64_t n = std::min<int64_t>(chunk, N - lo);
+    const int b = k & 1;
+    // rows lo .. lo + n - 1: the last row ends after n_pix elements, not after ld
+    const size_t in_bytes = ((size_t)(n - 1) * ld + n_pix) * isz;
+    if (k >= 2) OC_CUDA(cudaStreamWaitEvent(hp.copy, hp.freed[b], 0));  // encoder of chunk k - 2 is done with stage[b]
+    OC_CUDA(cudaMemcpyAsync(hp.stage[b].p, reinterpret_cast<const char*>(images_host) + (size_t)lo * ld * isz, in_bytes,
+                            cudaMemcpyHostToDevice, hp.copy));
+    OC_CUDA(cudaEventRecord(hp.copied[b], hp.copy));
+    OC_CUDA(cudaStreamWaitEvent(st, hp.copied[b], 0));
+    if (int rc = encode_impl(cx, hp.stage[b].p, in_dtype, n, n_pix, ld, L, D, dtype, trunc_mode, hp.mps.p, nullptr,
+                             nullptr, st))
+      return rc;
+    OC_CUDA(cudaEventRecord(hp.freed[b], st));
+    if (k >= 2) OC_CUDA(cudaStreamWaitEvent(st, hp.backdone[b], 0));  // results of chunk k - 2 have left ov[b] / am[b]
+    if (int rc = overlap_impl(cx, hp.mps.p, bonds, hp.clf.p, clf_bonds_host, clf_s_host, L, n, dtype, hp.ov[b].p,
+                              reinterpret_cast<int32_t*>(hp.am[b].p), st))
+      return rc;
+    OC_CUDA(cudaEventRecord(hp.done[b], st));
+    OC_CUDA(cudaStreamWaitEvent(hp.back, hp.done[b], 0));
+    OC_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(overlaps_out_host) + (size_t)lo * S * esz, hp.ov[b].p,
+                            (size_t)n * S * esz, cudaMemcpyDeviceToHost, hp.back));
+    if (argmax_out_host)
+      OC_CUDA(cudaMemcpyAsync(argmax_out_host + lo, hp.am[b].p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                              hp.back));
+    OC_CUDA(cudaEventRecord(hp.backdone[b], hp.back));
+  }
+  for (int b = 0; b < 2 && b < k; ++b) OC_CUDA(cudaStreamWaitEvent(st, hp.backdone[b], 0));
   OC_CUDA(cudaStreamSynchronize(st));
   return OC_OK;
 }

@@ -7,6 +7,19 @@ namespace oc {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Per-device "already done" flags (kernel attributes such as the > 48 KB shared-memory opt-in are
+// per device: a process that uses a second GPU must set them there too).
+constexpr int kMaxDevices = 64;
+struct PerDeviceFlag {
+  bool done[kMaxDevices] = {};
+  // returns the flag of the calling thread's current device
+  bool& cur() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return done[(dev >= 0 && dev < kMaxDevices) ? dev : 0];
+  }
+};
+
 template <typename T> struct Num;
 template <> struct Num<float> {
   // rotate a pair only if |a.b| > tol * |a||b|  (relative, Hestenes/de Rijk)

@@ -623,10 +623,6 @@ struct SplitStreams {
   cudaStream_t aux = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
-inline SplitStreams& split_streams() {
-  static SplitStreams s;
-  return s;
-}
 namespace hw {
 inline bool supported(const EncodeParams& P);
 inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, void* sort_ws, int64_t chunk,
@@ -634,7 +630,9 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
 }  // namespace hw
 
 // ws: 2 * min(N, kEncodeChunk) * kWsStride floats of device scratch.
-inline int encode_fast_launch(const EncodeParams& P0, float* ws, int sms, cudaStream_t st) {
+// split: the caller's (per device and stream) auxiliary stream for "enc_split2", nullable.
+inline int encode_fast_launch(const EncodeParams& P0, float* ws, int sms, cudaStream_t st,
+                              SplitStreams* split = nullptr) {
   int DP = 1;
   while (DP < P0.D) DP <<= 1;
   if (DP > 32) DP = 32;
@@ -658,10 +656,10 @@ inline int encode_fast_launch(const EncodeParams& P0, float* ws, int sms, cudaSt
     } restore{ev_on};
     if (encode_use_hw() && hw::supported(P)) {
       char* sort_ws = reinterpret_cast<char*>(ws + (size_t)2 * chunk * kWsStride);
-      if (encode_split2() && !ev_on && P.N >= 32768) {
+      if (split && encode_split2() && !ev_on && P.N >= 32768) {
         // two halves of the chunk on two streams: the CTAs of one half fill the SMs that the
         // last wave of the other half's kernel leaves idle (a Jacobi CTA lives 100-200 us)
-        SplitStreams& ss = split_streams();
+        SplitStreams& ss = *split;
         if (!ss.aux) {
           if ((e = cudaStreamCreateWithFlags(&ss.aux, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
           cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming);

@@ -662,7 +662,8 @@ inline cudaError_t launch_head(const EncodeParams& P, double* gws, float* ws_psi
   const int mode = pix_mode(P);
   auto launch = [&](auto mode_tag) -> cudaError_t {
     constexpr int MODE = decltype(mode_tag)::value;
-    static bool attr_set = false;
+    static PerDeviceFlag attr_flag;
+    bool& attr_set = attr_flag.cur();
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(gram_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
       if (e != cudaSuccess) return e;

@@ -1062,7 +1062,10 @@ inline size_t overlap_fast_scratch_floats(const OverlapParams& P) {
   return (size_t)((F.small_w_total + 31) & ~31) + (size_t)F.wc_elems;
 }
 
-inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int sms, cudaStream_t st) {
+// do_prep = false: scratch_dev already holds the re-laid classifier of an earlier call with the same
+// classifier contents, shapes and options (the caller's cache, see oc_classifier_cache)
+inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int sms, cudaStream_t st,
+                               bool do_prep = true) {
   OverlapFast F;
   if (!overlap_fast_plan(P, F)) return -1;
   float* small_w = scratch_dev;
@@ -1086,12 +1089,14 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   }
   const bool mma = (nat || pad) && overlap_mma() && warps == 8;
   const bool lmma = last && overlap_mma();
-  overlap_prep_kernel<float><<<1, 1024, 0, st>>>(reinterpret_cast<const float*>(P.clf), P, F, small_w, wc,
-                                                 lmma ? 0x60u : (mma ? 0x10u : 0u));
+  if (do_prep)
+    overlap_prep_kernel<float><<<1, 1024, 0, st>>>(reinterpret_cast<const float*>(P.clf), P, F, small_w, wc,
+                                                   lmma ? 0x60u : (mma ? 0x10u : 0u));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const size_t smem = wbytes + tabbytes + (size_t)warps * PER_WARP * 4;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;
+  bool& attr_set = attr_flag.cur();
   if (!attr_set) {
     e = cudaFuncSetAttribute(overlap_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return (int)e;

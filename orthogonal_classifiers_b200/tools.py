@@ -43,8 +43,9 @@ class SiteTensor:
 
 class OverlapResult:
     """What ``mps.H.squeeze() @ classifier.squeeze()`` evaluates to: a tensor
-    whose ``.data`` is the signed label vector (experiments.py:332-337 takes
-    ``np.abs`` of it)."""
+    whose ``.data`` is the label vector.  The reference's is signed and every
+    caller takes ``np.abs`` of it (experiments.py:332-337); the sign of an MPS
+    is a gauge choice, so here ``.data`` is already the non-negative vector."""
 
     def __init__(self, data):
         self.data = data
@@ -105,6 +106,8 @@ class MPSNetwork:
         form is ``label_overlaps``.  Returns the non-negative label vector
         (the sign of an MPS is a gauge choice; the reference takes np.abs)."""
         b = self._single_batch(None)
+        if isinstance(classifier, MPONetwork):  # reuse the packed device copy across calls
+            classifier = classifier.device_classifier(b.dtype)
         ov, _ = batched.overlaps_from_mps(b, classifier, return_argmax=False)
         return OverlapResult(ov[0].double().cpu().numpy())
 
@@ -144,14 +147,16 @@ MPS encoding tools
 """
 
 
-def image_to_mps(f_image, D, dtype="f32", trim=False):
+def image_to_mps(f_image, D, dtype="f32", trim=False, trunc=None):
     """tools.py:217-221.  ``trim=True`` removes zero trailing bond columns the
     way xmps' minD does (variable bonds per image); default keeps the fixed
-    natural profile, zero padded."""
+    natural profile, zero padded.  ``trunc``: which sweep truncates to D —
+    "sweep" (default: ``left_from_state(..).left_canonicalise(D)`` as the
+    reference calls it) or "inline" (batched.DEFAULT_TRUNC)."""
     f_image = np.asarray(f_image)
     if f_image.ndim != 1:
         raise ValueError("image_to_mps takes one flat image")
-    batch = batched.encode_images(f_image[None], D, dtype=dtype)
+    batch = batched.encode_images(f_image[None], D, dtype=dtype, trunc=trunc)
     L = batch.L
     Dmax = max(batch.bonds) if D is None else min(D, 2 ** (L // 2))
     return fMPS(batch.sites_numpy(0, trim=trim), D=Dmax if D is None else D)
@@ -192,7 +197,7 @@ def load_qtn_classifier(dir, root="Classifiers"):
     num_files = len(files)
     data = []
     for i in range(num_files):
-        site = np.load(os.path.join(path, f"site_{i}.npy"), allow_pickle=True)
+        site = np.load(os.path.join(path, f"site_{i}.npy"), allow_pickle=False)  # plain ndarrays: no pickle needed
         if i == 0:
             if len(site.shape) == 2:
                 site = np.expand_dims(np.expand_dims(site, 1), 1)

@@ -22,10 +22,11 @@ MPS Encoding
 """
 
 
-def mps_encoding(images, D=2, dtype="f32"):
+def mps_encoding(images, D=2, dtype="f32", trunc=None):
     """variational_mpo_classifiers.py:102-104 —
-    ``[fMPS_to_QTN(image_to_mps(image, D)) for image in images]``."""
-    batch = batched.encode_images(np.asarray(images), D, dtype=dtype)
+    ``[fMPS_to_QTN(image_to_mps(image, D)) for image in images]``.
+    ``trunc``: "sweep" (default, the reference's truncation order) or "inline"."""
+    batch = batched.encode_images(np.asarray(images), D, dtype=dtype, trunc=trunc)
     out = MPSList(MPSNetwork(batch=batch, index=i) for i in range(len(batch)))
     out.batch = batch
     return out

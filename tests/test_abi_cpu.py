@@ -76,6 +76,15 @@ def test_argument_errors_without_gpu():
     assert lib.oc_encode_batch(1, 0, 4, 784, 784, 9, 32, 0, 0, 1, None, None, None) == 1   # L mismatch
     assert lib.oc_encode_batch(1, 0, 4, 784, 100, 10, 32, 0, 0, 1, None, None, None) == 1  # ld < n_pix
     assert lib.oc_encode_batch(1, 0, 0, 784, 784, 10, 32, 0, 0, 1, None, None, None) == 0  # empty batch
+    assert lib.oc_encode_batch(1, 0, 4, 784, 784, 10, 32, 0, 2, 1, None, None, None) == 1  # unknown trunc_mode
+    assert lib.oc_encode_batch(1, 0, -1, 784, 784, 10, 32, 0, 1, 1, None, None, None) == 1  # N < 0
+    assert lib.oc_encode_batch(1, 0, 0, 784, 784, 10, 10, 0, 1, 1, None, None, None) == 0   # OC_TRUNC_SWEEP, empty
+    # oc_encode_classify / oc_classify_host validate before touching anything
+    assert lib.oc_encode_classify(1, 0, -5, 784, 784, 10, 32, 0, 0, 1, None, None, None, 1, None, None) == 1
+    assert lib.oc_encode_classify(1, 9, 5, 784, 784, 10, 32, 0, 0, 1, None, None, None, 1, None, None) == 1
+    assert lib.oc_encode_classify(1, 0, 5, 784, 784, 10, 32, 5, 0, 1, None, None, None, 1, None, None) == 1
+    assert lib.oc_classify_host(1, 0, -5, 784, 784, 10, 32, 0, 0, 1, 10, None, None, 1, None, None) == 1
+    assert lib.oc_classify_host(1, 0, 5, 784, 784, 77, 32, 0, 0, 1, 10, None, None, 1, None, None) == 1
     assert lib.oc_set_option(b"nope", 1) == 1
     with pytest.raises(_lib.OcError):
         _lib.check(lib.oc_set_option(b"nope", 1))

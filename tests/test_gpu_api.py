@@ -1,0 +1,204 @@
+"""GPU tests of the entry points either side of the kernels: the host-buffer C-ABI
+call, the generic-L overlap (MPS stacking shapes), classifier files, trimming,
+and the per-(device, stream) library state."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from orthogonal_classifiers_b200.synthetic import (adversarial_images, random_classifier,
+                                                    synthetic_images)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f32": 1e-5, "f64": 1e-10}
+
+
+def _random_mps(rng, bonds, n):
+    """n random (not normalised, not canonical) MPSs with the given bond profile, packed
+    the way include/oc_b200.h lays a batch out."""
+    sites = [[rng.standard_normal((2, a, b)) / np.sqrt(a) for a, b in zip(bonds[:-1], bonds[1:])] for _ in range(n)]
+    flat = np.stack([np.concatenate([s.reshape(-1) for s in img]) for img in sites])
+    return sites, flat
+
+
+def _random_mpo(rng, bonds, c, S):
+    return [rng.standard_normal((2, S if n == c else 1, a, b)) / np.sqrt(2 * a)
+            for n, (a, b) in enumerate(zip(bonds[:-1], bonds[1:]))]
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+@pytest.mark.parametrize("L,c,amax,Bmax", [(4, 0, 4, 4), (4, 3, 4, 4), (4, 1, 2, 4), (8, 2, 8, 16), (8, 7, 16, 16),
+                                           (16, 8, 8, 32), (16, 0, 4, 8), (16, 15, 32, 32), (12, 5, 16, 12),
+                                           (20, 13, 6, 10), (64, 40, 4, 4)])
+def test_overlap_any_length_and_hairy_site(gpu_lib, dtype, L, c, amax, Bmax):
+    """The contraction of experiments.py:633 (MPS stacking: L = 4 (n + 1) sites, label leg
+    wherever the stacking MPO carries it) — chains of 4..64 sites, the hairy site at the
+    ends and in the middle, image and classifier bonds unrelated."""
+    import torch
+    from orthogonal_classifiers_b200 import batched
+    rng = np.random.default_rng(L * 100 + c)
+    a = [min(2 ** n, 2 ** (L - n), amax) for n in range(L + 1)]
+    B = [min(2 ** n, 2 ** (L - n), Bmax) for n in range(L + 1)]
+    n_img = 37
+    sites, flat = _random_mps(rng, a, n_img)
+    clf = _random_mpo(rng, B, c, 16)
+    offs = np.concatenate([[0], np.cumsum([2 * x * y for x, y in zip(a[:-1], a[1:])])]).tolist()
+    tdt = torch.float32 if dtype == "f32" else torch.float64
+    mps = batched.MPSBatch(torch.from_numpy(flat).to(tdt).cuda(), a, offs, L, None, dtype)
+    ov, am = batched.overlaps_from_mps(mps, clf)
+    ov = ov.double().cpu().numpy()
+    ref = np.array([oracle.overlaps_chain(s, clf) for s in sites])
+    assert ov.shape == ref.shape == (n_img, 16)
+    # a random chain of L sites has entries of very different size: compare relative to the
+    # largest overlap of the batch, as everywhere
+    assert np.abs(ov - ref).max() <= TOL[dtype] * ref.max()
+    srt = np.sort(ref, axis=1)
+    tie = (srt[:, -1] - srt[:, -2]) < 4 * TOL[dtype] * ref.max()
+    assert np.all((am.cpu().numpy() == ref.argmax(1)) | tie)
+
+
+@pytest.mark.parametrize("in_dtype", [np.float32, np.float64, np.uint8])
+def test_classify_host_c_abi(gpu_lib, in_dtype):
+    """oc_classify_host: host buffers in and out through one C-ABI call; the pipelined
+    chunks (pinned and pageable memory, ragged last chunk, row stride > n_pix) give
+    exactly what the device-pointer entry points give."""
+    import torch
+    from orthogonal_classifiers_b200 import batched
+    base = np.concatenate([synthetic_images(1000, seed=31), adversarial_images()])
+    if in_dtype == np.uint8:
+        imgs = np.rint(base * 255).astype(np.uint8)
+    else:
+        imgs = base.astype(in_dtype)
+    clf = gpu_lib.DeviceClassifier(random_classifier(10, 32, centre=5, seed=2))
+    ref_ov, ref_am = gpu_lib.classify(imgs, clf, 32)
+    try:
+        for chunk in (0, 300, 5000):
+            batched.set_option("host_chunk", chunk)
+            ov, am = gpu_lib.classify_host(imgs, clf, 32)
+            np.testing.assert_array_equal(ov.astype(np.float64), ref_ov)
+            np.testing.assert_array_equal(am, ref_am)
+        batched.set_option("host_chunk", 256)
+        pin = torch.from_numpy(imgs).pin_memory()
+        ovp = torch.empty((len(imgs), 16), dtype=torch.float32).pin_memory()
+        amp = torch.empty((len(imgs),), dtype=torch.int32).pin_memory()
+        for _ in range(2):
+            ovp.zero_(); amp.zero_()
+            gpu_lib.classify_host(pin, clf, 32, out=(ovp, amp))
+            np.testing.assert_array_equal(ovp.numpy().astype(np.float64), ref_ov)
+            np.testing.assert_array_equal(amp.numpy(), ref_am)
+        # rows with a stride: the last row must not be read past its n_pix pixels
+        wide = np.zeros((len(imgs), 800), dtype=in_dtype)
+        wide[:, :784] = imgs
+        ovw, amw = gpu_lib.classify_host(wide[:, :784], clf, 32)
+        np.testing.assert_array_equal(ovw.astype(np.float64), ref_ov)
+        # truncated encoders and fp64 through the same call
+        for D, trunc in ((10, "sweep"), (10, "inline")):
+            r_ov, r_am = gpu_lib.classify(imgs[:300], clf, D, trunc=trunc)
+            ov, am = gpu_lib.classify_host(imgs[:300], clf, D, trunc=trunc)
+            np.testing.assert_array_equal(ov.astype(np.float64), r_ov)
+        clf64 = gpu_lib.DeviceClassifier(random_classifier(10, 32, centre=5, seed=2), dtype="f64")
+        r_ov, _ = gpu_lib.classify(imgs[:200], clf64, 32, dtype="f64")
+        ov, _ = gpu_lib.classify_host(imgs[:200], clf64, 32, dtype="f64")
+        np.testing.assert_array_equal(ov, r_ov)
+    finally:
+        batched.set_option("host_chunk", 0)
+    # argument errors come back as codes, not crashes
+    from orthogonal_classifiers_b200 import _lib
+    assert _lib.lib.oc_classify_host(imgs.ctypes.data, 7, 4, 784, 784, 10, 32, 0, 0, clf.packed_host.ctypes.data,
+                                     clf.packed_host.size, clf._bonds_c, clf._s_c, ref_ov.ctypes.data, None, None) == 1
+    assert _lib.lib.oc_classify_host(imgs.ctypes.data, 0, -3, 784, 784, 10, 32, 0, 0, clf.packed_host.ctypes.data,
+                                     clf.packed_host.size, clf._bonds_c, clf._s_c, ref_ov.ctypes.data, None, None) == 1
+
+
+def test_classifier_files_round_trip(gpu_lib, golden, tmp_path):
+    """tools.py:262-291: save one ``site_{i}.npy`` per site, load them back (squeezed
+    dimensions re-expanded), classify with the loaded classifier."""
+    from conftest import golden_sites
+    clf = golden_sites(golden, "clf_e32_b32_f32_ortho")
+    q = gpu_lib.data_to_QTN(clf)
+    gpu_lib.save_qtn_classifier(q, "round_trip", root=str(tmp_path))
+    assert sorted(os.listdir(tmp_path / "round_trip")) == sorted(f"site_{i}.npy" for i in range(10))
+    back = gpu_lib.load_qtn_classifier("round_trip", root=str(tmp_path))
+    for a, b in zip(back.data, clf):
+        np.testing.assert_array_equal(a, b)
+    # the reference saves the SQUEEZED network (experiments.py / tools.py:262-266): edge bonds
+    # and the size-1 label legs are gone; the loader puts them back
+    sq = [np.squeeze(w) if n != 5 else w.reshape(2, 16, 32, 16) for n, w in enumerate(clf)]
+    os.makedirs(tmp_path / "squeezed")
+    for i, w in enumerate(sq):
+        np.save(tmp_path / "squeezed" / f"site_{i}", w)
+    back2 = gpu_lib.load_qtn_classifier("squeezed", root=str(tmp_path))
+    assert [w.shape for w in back2.data] == [w.shape for w in clf]
+    ov, _ = gpu_lib.classify(golden["x_test"], back2, 32)
+    ref = golden["pred_e32_b32_f32_ortho"]
+    assert np.abs(ov - ref).max() <= 1e-5 * ref.max()
+
+
+def test_image_to_mps_trim_and_structure(gpu_lib):
+    """tools.py:217-221 / test_tools.py:238-248: L = ceil(log2(784)) = 10, d = 2, D as asked;
+    ``trim=True`` drops the zero trailing bond columns (xmps' minD) without changing the state."""
+    imgs = np.concatenate([synthetic_images(3, seed=7), adversarial_images()[1:3]])
+    for im in imgs:
+        for D in (32, 10, 2):
+            full = gpu_lib.image_to_mps(im, D, dtype="f64")
+            trim = gpu_lib.image_to_mps(im, D, dtype="f64", trim=True)
+            assert full.L == trim.L == 10 and full.d == 2 and full.D == D
+            a = oracle.mps_to_state(full.data)
+            b = oracle.mps_to_state(trim.data)
+            assert np.abs(a - b).max() < 1e-12
+            assert all(t.shape[1] <= f.shape[1] and t.shape[2] <= f.shape[2] for t, f in zip(trim.data, full.data))
+            ref, _ = oracle.encode_image(im, D, "sweep")
+            # the oracle trims by numerical rank exactly as xmps' minD: same bond dimensions
+            assert [t.shape for t in trim.data] == [r.shape for r in ref]
+    single = gpu_lib.image_to_mps(adversarial_images()[1], 32, dtype="f64", trim=True)
+    assert max(max(t.shape[1:]) for t in single.data) == 1      # a one-pixel image is a product state
+
+
+def test_streams_do_not_share_scratch(gpu_lib):
+    """Library state is keyed by (device, stream): two streams working at the same time on
+    different batches (different sizes, so their workspaces differ) give what each gives alone."""
+    import torch
+    from orthogonal_classifiers_b200 import batched
+    a = torch.from_numpy(synthetic_images(20000, seed=51).astype(np.float32)).cuda()
+    b = torch.from_numpy(synthetic_images(9000, seed=52).astype(np.float32)).cuda()
+    clf = gpu_lib.DeviceClassifier(random_classifier(10, 32, centre=5, seed=6))
+    ref_a = [t.clone() for t in batched.classify_device(a, clf, 32)]
+    ref_b = [t.clone() for t in batched.classify_device(b, clf, 10)]
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            ra = batched.classify_device(a, clf, 32)
+        with torch.cuda.stream(s2):
+            rb = batched.classify_device(b, clf, 10)
+        outs.append((ra, rb))
+    torch.cuda.synchronize()
+    for ra, rb in outs:
+        assert torch.equal(ra[0], ref_a[0]) and torch.equal(ra[1], ref_a[1])
+        assert torch.equal(rb[0], ref_b[0]) and torch.equal(rb[1], ref_b[1])
+    from orthogonal_classifiers_b200._lib import check, lib
+    check(lib.oc_release(int(s1.cuda_stream)))
+    check(lib.oc_release(int(s2.cuda_stream)))
+
+
+def test_classifier_cache_follows_content_changes(gpu_lib):
+    """oc_classifier_cache: the re-laid classifier is reused across calls; a DeviceClassifier built
+    at the same address with other contents, or other image bond profiles, must not see stale data."""
+    imgs = synthetic_images(64, seed=53).astype(np.float32)
+    for seed in (1, 2, 3):
+        sites = random_classifier(10, 32, centre=5, seed=seed)
+        clf = gpu_lib.DeviceClassifier(sites)
+        W = oracle.dense_classifier(sites)
+        ref = oracle.overlaps_dense(imgs.astype(np.float64), W)
+        for _ in range(2):
+            ov, _ = gpu_lib.classify(imgs, clf, 32)
+            assert np.abs(ov - ref).max() <= 1e-5 * ref.max()
+        b10 = gpu_lib.encode_images(imgs, 10)
+        ov10 = gpu_lib.label_overlaps(b10, clf)
+        ref10 = np.array([oracle.overlaps_chain([s.astype(np.float64) for s in b10.sites_numpy(i)], sites)
+                          for i in range(len(imgs))])
+        assert np.abs(ov10 - ref10).max() <= 1e-5 * ref10.max()
+        del clf
