@@ -204,6 +204,8 @@ def load_qtn_classifier(dir, root="Classifiers"):
             if len(site.shape) == 3:
                 site = np.expand_dims(site, 2)
         elif i == num_files - 1:
+            if len(site.shape) == 2:  # (d, Bl): a squeezed non-hairy last site (centre-hairy
+                site = np.expand_dims(site, 1)  # classifiers; the reference's loader stops at 3-d)
             if len(site.shape) == 3:
                 site = np.expand_dims(site, -1)
         else:
