@@ -85,6 +85,7 @@ const char* oc_last_error(void);
  *   "enc_events"    see oc_encode_step_ms
  *   "host_chunk" = n  images per pipeline stage of oc_classify_host (0 = default: 17,500 for
  *                   float pixels, 35,000 for uint8)
+ *   "host_ramp" = 0 uint8 input: equal stages instead of the ramp chunk/4, chunk/2, chunk, ...
  * Unknown keys return OC_E_ARG. */
 int oc_set_option(const char* key, int value);
 
@@ -136,6 +137,40 @@ int oc_overlap_batch(const void* mps_dev, const int32_t* mps_bonds_host,
                      const int32_t* clf_s_host, int L, int64_t N, int dtype,
                      void* overlaps_out_dev, int32_t* argmax_out_dev,
                      void* stream);
+
+/* As oc_overlap_batch, but overlaps_out_dev receives the SIGNED label vector
+ * (mps.H @ classifier).data before the np.abs (defined up to one global sign per
+ * image, the sign of the MPS being a gauge choice); argmax_out is still the argmax
+ * of the absolute values.  Input of oc_label_mix. */
+int oc_overlap_batch_signed(const void* mps_dev, const int32_t* mps_bonds_host,
+                            const void* clf_dev, const int32_t* clf_bonds_host,
+                            const int32_t* clf_s_host, int L, int64_t N, int dtype,
+                            void* overlaps_out_dev, int32_t* argmax_out_dev, void* stream);
+
+/* Replaces the per-image, per-bitstring loops of
+ * variational_mpo_classifiers.py:309-318 (classifier_predictions with arbitrary
+ * product bitstrings) and :334-337 (padded_classifier_predictions):
+ *   out[i][l] = sum_{p < n_sum} | sum_{j < S} signed[i][j] * V[j][p * n_out + l] |
+ *   signed_dev  N x S signed label vectors (oc_overlap_batch_signed)
+ *   V_dev       S x (n_out * n_sum), row-major: column m = bitstring m's vector on the
+ *               hairy site times the product of its entries on the other sites
+ *   out_dev     N x n_out */
+int oc_label_mix(const void* signed_dev, int64_t N, int S, const void* V_dev, int n_out,
+                 int n_sum, int dtype, void* out_dev, void* stream);
+
+/* Replaces variational_mpo_classifiers.py:321-332 (ensemble_predictions: every
+ * member's label vector normalised to sum 1) and the k = 1 case of :348-363
+ * (evaluate_soft / evaluate_hard_ensemble_top_k_accuracy) up to the final count:
+ *   pred_dev        K x N x S |overlaps| of the K members (labels 0..n_labels-1 used)
+ *   norm_out_dev    nullable, K x N x n_labels normalised predictions
+ *   soft_out_dev    nullable, N x n_labels sum over members of the normalised rows
+ *   soft_argmax_dev nullable, N int32: argmax of that sum
+ *   hard_argmax_dev nullable, N int32: the label most members rank first (ties: the
+ *                   label whose first voter comes first, as Counter.most_common)
+ * Feed the argmax arrays to oc_count_correct for the accuracies. */
+int oc_ensemble_vote(const void* pred_dev, int K, int64_t N, int S, int n_labels, int dtype,
+                     void* norm_out_dev, void* soft_out_dev, int32_t* soft_argmax_dev,
+                     int32_t* hard_argmax_dev, void* stream);
 
 /* encode + classify for one batch without the caller handling the MPS:
  * `workspace_dev` must hold N * site_offsets[L] elements of `dtype`

@@ -66,7 +66,48 @@ def _combine(left, right):
     return out
 
 
+def _contract_pairwise(tensors):
+    """Greedy pairwise contraction for networks with more than 52 distinct indices (einsum's
+    alphabet): always contract the pair sharing an index whose result is smallest."""
+    cnt = {}
+    for t in tensors:
+        for i in t.inds:
+            cnt[i] = cnt.get(i, 0) + 1
+    out_inds = [i for t in tensors for i in t.inds if cnt[i] == 1]
+    ts = [(np.asarray(t.data), list(t.inds)) for t in tensors]
+    while len(ts) > 1:
+        best = None
+        for a in range(len(ts)):
+            for b in range(a + 1, len(ts)):
+                shared = [i for i in ts[a][1] if i in ts[b][1]]
+                if not shared:
+                    continue
+                size = 1
+                for d, i in zip(ts[a][0].shape, ts[a][1]):
+                    if i not in shared:
+                        size *= d
+                for d, i in zip(ts[b][0].shape, ts[b][1]):
+                    if i not in shared:
+                        size *= d
+                if best is None or size < best[0]:
+                    best = (size, a, b, shared)
+        if best is None:  # disconnected pieces: outer product of the first two
+            a, b, shared = 0, 1, []
+        else:
+            _, a, b, shared = best
+        (da, ia), (db, ib) = ts[a], ts[b]
+        data = np.tensordot(da, db, axes=([ia.index(i) for i in shared], [ib.index(i) for i in shared]))
+        inds = [i for i in ia if i not in shared] + [i for i in ib if i not in shared]
+        ts = [t for k, t in enumerate(ts) if k not in (a, b)] + [(data, inds)]
+    data, inds = ts[0]
+    if not out_inds:
+        return data.item() if data.ndim == 0 else data
+    return Tensor(np.transpose(data, [inds.index(i) for i in out_inds]), out_inds)
+
+
 def _contract(tensors):
+    if len({i for t in tensors for i in t.inds}) > 52:
+        return _contract_pairwise(tensors)
     names = {}
     letters = itertools.chain("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ")
     for t in tensors:

@@ -254,22 +254,59 @@ def _as_classifier(classifier, dtype: str, device=None) -> DeviceClassifier:
     return DeviceClassifier(sites, dtype=dtype, device=device)
 
 
-def overlaps_from_mps(mps: MPSBatch, classifier, return_argmax: bool = True):
-    """Device tensors (N, S) |overlap| and (N,) int32 argmax."""
+def overlaps_from_mps(mps: MPSBatch, classifier, return_argmax: bool = True, signed: bool = False, out=None):
+    """Device tensors (N, S) |overlap| and (N,) int32 argmax.  ``signed``: the signed label
+    vector (defined up to one global sign per image) instead of its absolute values.
+    ``out``: optional (N, S) device tensor to write into."""
     clf = _as_classifier(classifier, mps.dtype, mps.data.device)
     if clf.L != mps.L:
         raise ValueError(f"classifier has {clf.L} sites, images have {mps.L}")
     N = len(mps)
     dev = mps.data.device
-    ov = torch.empty((N, clf.S), dtype=_TORCH_DT[mps.dtype], device=dev)
+    ov = torch.empty((N, clf.S), dtype=_TORCH_DT[mps.dtype], device=dev) if out is None else out
     am = torch.empty((N,), dtype=torch.int32, device=dev) if return_argmax else None
+    fn = lib.oc_overlap_batch_signed if signed else lib.oc_overlap_batch
     with torch.cuda.device(dev):
         clf.cache_on_stream(_stream_ptr())
-        check(lib.oc_overlap_batch(
+        check(fn(
             mps.data.data_ptr(), i32_array(mps.bonds), clf.packed.data_ptr(), clf._bonds_c, clf._s_c,
             mps.L, N, _OC_DT[mps.dtype], ov.data_ptr(), am.data_ptr() if am is not None else None,
             _stream_ptr()))
     return ov, am
+
+
+def label_mix(signed_ov: torch.Tensor, V, n_out: int, n_sum: int = 1) -> torch.Tensor:
+    """``out[i, l] = sum_p | signed_ov[i] . V[:, p * n_out + l] |`` on the device
+    (``oc_label_mix``): the label legs contracted with n_out * n_sum product bitstrings
+    at once.  V: (S, n_out * n_sum) host array."""
+    N, S = signed_ov.shape
+    dt = "f64" if signed_ov.dtype == torch.float64 else "f32"
+    Vd = torch.as_tensor(np.ascontiguousarray(V, dtype=_NP_DT[dt])).to(signed_ov.device)
+    if Vd.shape != (S, n_out * n_sum):
+        raise ValueError(f"V must be ({S}, {n_out * n_sum}), got {tuple(Vd.shape)}")
+    out = torch.empty((N, n_out), dtype=signed_ov.dtype, device=signed_ov.device)
+    with torch.cuda.device(signed_ov.device):
+        check(lib.oc_label_mix(signed_ov.data_ptr(), N, S, Vd.data_ptr(), n_out, n_sum, _OC_DT[dt],
+                               out.data_ptr(), _stream_ptr()))
+    return out
+
+
+def ensemble_vote(pred: torch.Tensor, n_labels: int, want_norm: bool = True):
+    """``oc_ensemble_vote`` on a (K, N, S) device tensor of member |overlaps|: returns
+    (normalised (K, N, n_labels) or None, soft sum (N, n_labels), soft argmax (N,), hard
+    argmax (N,)) as device tensors."""
+    K, N, S = pred.shape
+    dt = "f64" if pred.dtype == torch.float64 else "f32"
+    dev = pred.device
+    norm = torch.empty((K, N, n_labels), dtype=pred.dtype, device=dev) if want_norm else None
+    soft = torch.empty((N, n_labels), dtype=pred.dtype, device=dev)
+    sa = torch.empty((N,), dtype=torch.int32, device=dev)
+    ha = torch.empty((N,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.oc_ensemble_vote(pred.data_ptr(), K, N, S, n_labels, _OC_DT[dt],
+                                   norm.data_ptr() if norm is not None else None, soft.data_ptr(),
+                                   sa.data_ptr(), ha.data_ptr(), _stream_ptr()))
+    return norm, soft, sa, ha
 
 
 def classify_device(images_dev: torch.Tensor, clf: DeviceClassifier, D: int | None,

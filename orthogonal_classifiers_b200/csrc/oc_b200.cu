@@ -129,6 +129,7 @@ std::mutex g_ctx_mu;
 std::map<std::pair<int, void*>, std::unique_ptr<Ctx>> g_ctx;
 int g_force_generic = 0;
 int g_host_chunk = 0;  // 0 = default per input type
+int g_host_ramp = 1;
 
 Ctx& get_ctx(cudaStream_t st) {
   int dev = 0;
@@ -287,9 +288,16 @@ int encode_sweep_t(Ctx& cx, const void* images_dev, int in_dtype, int64_t N, int
     if (int rc = cx.sw_sv.ensure((size_t)chunk * L * S.sv_width * sizeof(T), st)) return rc;
   if (sweeps_out_dev)
     if (int rc = cx.sw_sw.ensure((size_t)chunk * L * sizeof(int32_t), st)) return rc;
-  const int warps = sizeof(T) == 8 ? 2 : 4;
-  const size_t smem = (size_t)warps * oc::sweep::kSwPerWarp * sizeof(T);
-  if (int rc = set_smem(oc::sweep::sweep_back_kernel<T>, smem)) return rc;
+  // lanes per image = the smallest of 8 / 16 / 32 that holds the largest bond
+  int amax = 1;
+  for (int n = 0; n <= L; ++n) amax = std::max(amax, S.bonds[n]);
+  const int G = amax <= 8 ? 8 : (amax <= 16 ? 16 : 32);
+  const int ipw = 32 / G;
+  const int warps = (sizeof(T) == 8 && G == 32) ? 2 : 4;
+  const size_t smem = (size_t)warps * ipw * oc::sweep::sw_per_image(G) * sizeof(T);
+  auto kern = G == 8 ? oc::sweep::sweep_back_kernel<T, 8>
+                     : (G == 16 ? oc::sweep::sweep_back_kernel<T, 16> : oc::sweep::sweep_back_kernel<T, 32>);
+  if (int rc = set_smem(kern, smem)) return rc;
   for (int64_t lo = 0; lo < N; lo += kSweepChunk) {
     const int64_t n = std::min<int64_t>(kSweepChunk, N - lo);
     const char* src = reinterpret_cast<const char*>(images_dev) + (size_t)lo * ld * in_esz;
@@ -308,9 +316,9 @@ int encode_sweep_t(Ctx& cx, const void* images_dev, int in_dtype, int64_t N, int
     S.tmp_sw = sweeps_out_dev ? reinterpret_cast<const int32_t*>(cx.sw_sw.p) : nullptr;
     S.sw_out = sweeps_out_dev ? sweeps_out_dev + (size_t)lo * L : nullptr;
     S.N = n;
-    const int64_t need = (n + warps - 1) / warps;
+    const int64_t need = (n + (int64_t)warps * ipw - 1) / ((int64_t)warps * ipw);
     const int grid = (int)std::min<int64_t>(need, (int64_t)num_sms() * 16);
-    oc::sweep::sweep_back_kernel<T><<<grid, warps * 32, smem, st>>>(S);
+    kern<<<grid, warps * 32, smem, st>>>(S);
     OC_CUDA(cudaGetLastError());
   }
   return OC_OK;
@@ -342,7 +350,7 @@ uint64_t fnv(uint64_t h, const void* p, size_t n) {
 
 int overlap_impl(Ctx& cx, const void* mps_dev, const int32_t* mps_bonds_host, const void* clf_dev,
                  const int32_t* clf_bonds_host, const int32_t* clf_s_host, int L, int64_t N, int dtype,
-                 void* overlaps_out_dev, int32_t* argmax_out_dev, cudaStream_t st) {
+                 void* overlaps_out_dev, int32_t* argmax_out_dev, cudaStream_t st, int signed_out = 0) {
   if (N < 0) return fail(OC_E_ARG, "N=%lld < 0", (long long)N);
   if (L < 1 || L > OC_MAX_SITES) return fail(OC_E_ARG, "L=%d outside [1,%d]", L, OC_MAX_SITES);
   if (dtype != OC_F32 && dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", dtype);
@@ -387,6 +395,7 @@ int overlap_impl(Ctx& cx, const void* mps_dev, const int32_t* mps_bonds_host, co
   P.mps_stride = mo;
   P.overlaps = overlaps_out_dev;
   P.argmax = argmax_out_dev;
+  P.signed_out = signed_out;
 
   if (dtype == OC_F32 && !g_force_generic && oc::overlap_fast_supported(P)) {
     const size_t bytes = oc::overlap_fast_scratch_floats(P) * sizeof(float);
@@ -454,6 +463,10 @@ int oc_set_option(const char* key, int value) {
   }
   if (key && !strcmp(key, "host_chunk") && value >= 0) {
     g_host_chunk = value;
+    return OC_OK;
+  }
+  if (key && !strcmp(key, "host_ramp")) {
+    g_host_ramp = value;
     return OC_OK;
   }
   if (key && !strcmp(key, "enc_events")) {
@@ -534,6 +547,64 @@ int oc_overlap_batch(const void* mps_dev, const int32_t* mps_bonds_host, const v
   std::lock_guard<std::mutex> lk(cx.mu);
   return overlap_impl(cx, mps_dev, mps_bonds_host, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype,
                       overlaps_out_dev, argmax_out_dev, st);
+}
+
+int oc_overlap_batch_signed(const void* mps_dev, const int32_t* mps_bonds_host, const void* clf_dev,
+                            const int32_t* clf_bonds_host, const int32_t* clf_s_host, int L, int64_t N,
+                            int dtype, void* overlaps_out_dev, int32_t* argmax_out_dev, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Ctx& cx = get_ctx(st);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  return overlap_impl(cx, mps_dev, mps_bonds_host, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype,
+                      overlaps_out_dev, argmax_out_dev, st, 1);
+}
+
+int oc_label_mix(const void* signed_dev, int64_t N, int S, const void* V_dev, int n_out, int n_sum, int dtype,
+                 void* out_dev, void* stream) {
+  if (N < 0 || S < 1 || S > OC_MAX_LABEL || n_out < 1 || n_sum < 1) return fail(OC_E_ARG, "bad sizes");
+  if (dtype != OC_F32 && dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", dtype);
+  if (N == 0) return OC_OK;
+  if (!signed_dev || !V_dev || !out_dev) return fail(OC_E_ARG, "null pointer argument");
+  const size_t esz = dtype == OC_F32 ? 4 : 8;
+  const size_t smem = (size_t)S * n_out * n_sum * esz;
+  if (smem > 48 * 1024) return fail(OC_E_ARG, "%d x %d bitstrings do not fit shared memory", n_out, n_sum);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const int grid = (int)std::min<int64_t>((N * n_out + threads - 1) / threads, (int64_t)num_sms() * 8);
+  if (dtype == OC_F32)
+    oc::label_mix_kernel<float><<<grid, threads, smem, st>>>(reinterpret_cast<const float*>(signed_dev), N, S,
+                                                            reinterpret_cast<const float*>(V_dev), n_out, n_sum,
+                                                            reinterpret_cast<float*>(out_dev));
+  else
+    oc::label_mix_kernel<double><<<grid, threads, smem, st>>>(reinterpret_cast<const double*>(signed_dev), N, S,
+                                                             reinterpret_cast<const double*>(V_dev), n_out, n_sum,
+                                                             reinterpret_cast<double*>(out_dev));
+  OC_CUDA(cudaGetLastError());
+  return OC_OK;
+}
+
+int oc_ensemble_vote(const void* pred_dev, int K, int64_t N, int S, int n_labels, int dtype, void* norm_out_dev,
+                     void* soft_out_dev, int32_t* soft_argmax_dev, int32_t* hard_argmax_dev, void* stream) {
+  if (K < 1 || N < 0 || S < 1 || n_labels < 1 || n_labels > S || n_labels > OC_MAX_LABEL)
+    return fail(OC_E_ARG, "bad sizes (K=%d, S=%d, n_labels=%d)", K, S, n_labels);
+  if (dtype != OC_F32 && dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", dtype);
+  if (N == 0) return OC_OK;
+  if (!pred_dev) return fail(OC_E_ARG, "null pointer argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int threads = 128;
+  const int grid = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)num_sms() * 16);
+  if (dtype == OC_F32)
+    oc::ensemble_vote_kernel<float><<<grid, threads, 0, st>>>(reinterpret_cast<const float*>(pred_dev), K, N, S, n_labels,
+                                                             reinterpret_cast<float*>(norm_out_dev),
+                                                             reinterpret_cast<float*>(soft_out_dev), soft_argmax_dev,
+                                                             hard_argmax_dev);
+  else
+    oc::ensemble_vote_kernel<double><<<grid, threads, 0, st>>>(reinterpret_cast<const double*>(pred_dev), K, N, S,
+                                                              n_labels, reinterpret_cast<double*>(norm_out_dev),
+                                                              reinterpret_cast<double*>(soft_out_dev), soft_argmax_dev,
+                                                              hard_argmax_dev);
+  OC_CUDA(cudaGetLastError());
+  return OC_OK;
 }
 
 int oc_encode_classify(const void* images_dev, int in_dtype, int64_t N, int n_pix, int64_t ld,
@@ -684,9 +755,29 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
         OC_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
   // chunk schedule: the copy of chunk k + 1 runs under the kernels of chunk k.  Defaults measured on
-  // B200; oc_set_option("host_chunk", n) overrides.
-  int64_t chunk = g_host_chunk > 0 ? g_host_chunk : (in_dtype == OC_U8 ? 35000 : 17500);
-  chunk = std::min<int64_t>(chunk, N);
+  // B200; oc_set_option("host_chunk", n) overrides.  When the kernels, not the copy,
+  // bound the pipeline (uint8 pixels: 0.75 KB per image) the schedule ramps up - chunk / 4, chunk / 2,
+  // then full chunks - so that the first kernels start after a short copy.
+  const int64_t base = std::min<int64_t>(g_host_chunk > 0 ? g_host_chunk : (in_dtype == OC_U8 ? 35000 : 17500), N);
+  std::vector<int64_t> sizes;
+  {
+    int64_t left = N;
+    if (in_dtype == OC_U8 && g_host_ramp && base >= 4096) {
+      for (int64_t c : {base / 4, base / 2}) {
+        if (left > c + base / 2) {
+          sizes.push_back(c);
+          left -= c;
+        }
+      }
+    }
+    while (left > 0) {
+      int64_t c = std::min(base, left);
+      if (left - c < base / 2) c = left;  // no short last chunk: its kernels would run at low occupancy
+      sizes.push_back(c);
+      left -= c;
+    }
+  }
+  const int64_t chunk = *std::max_element(sizes.begin(), sizes.end());
   for (int b = 0; b < 2; ++b) {
     if (int rc = hp.stage[b].ensure((size_t)chunk * ld * isz, st)) return rc;
     if (int rc = hp.ov[b].ensure((size_t)chunk * S * esz, st)) return rc;
@@ -696,8 +787,9 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
   if (int rc = hp.mps.ensure((size_t)chunk * offs[L] * esz, st)) return rc;
   OC_CUDA(cudaMemcpyAsync(hp.clf.p, clf_packed_host, (size_t)clf_elems * esz, cudaMemcpyHostToDevice, st));
   int k = 0;
-  for (int64_t lo = 0; lo < N; lo += chunk, ++k) {
-    const int64_t n = std::min<int64_t>(chunk, N - lo);
+  int64_t lo = 0;
+  for (; k < (int)sizes.size(); lo += sizes[k], ++k) {
+    const int64_t n = sizes[k];
     const int b = k & 1;
     // rows lo .. lo + n - 1: the last row ends after n_pix elements, not after ld
     const size_t in_bytes = ((size_t)(n - 1) * ld + n_pix) * isz;

@@ -238,6 +238,7 @@ struct OverlapParams {
   int B[OC_MAX_SITES + 1];
   void* overlaps;
   int32_t* argmax;  // nullable
+  int signed_out;   // 1: store the signed label vector instead of its absolute values (argmax still on |.|)
 };
 
 template <typename T>
@@ -343,21 +344,105 @@ __global__ void __launch_bounds__(128) overlap_generic_kernel(const __grid_const
       for (int l = 0; l < OC_MAX_LABEL; ++l) {
         if (l < P.S) {
           T v = warp_sum(acc_l[l]);
-          if (lane == 0) outv[l] = Num<T>::abs(v);
+          if (lane == 0) outv[l] = v;
         }
       }
       __syncwarp();
       T* ov = reinterpret_cast<T*>(P.overlaps) + (size_t)img * P.S;
-      for (int l = lane; l < P.S; l += 32) ov[l] = outv[l];
+      for (int l = lane; l < P.S; l += 32) ov[l] = P.signed_out ? outv[l] : Num<T>::abs(outv[l]);
       if (P.argmax && lane == 0) {
         int best = 0;
-        T bv = outv[0];
+        T bv = Num<T>::abs(outv[0]);
         for (int l = 1; l < P.S; ++l)
-          if (outv[l] > bv) { bv = outv[l]; best = l; }
+          if (Num<T>::abs(outv[l]) > bv) { bv = Num<T>::abs(outv[l]); best = l; }
         P.argmax[img] = best;
       }
     }
     __syncwarp();
+  }
+}
+
+// out[i][m] (+)= | sum_j signed[i][j] * V[j][m] |  : the label legs of a one-hairy-site classifier
+// contracted with M product bitstrings at once (variational_mpo_classifiers.py:313, 334-337:
+// ``abs(img.H @ (clf @ bitstring))``; V[:, m] = bitstring m's vector on the hairy site times the
+// product of its size-1 entries on the other sites).  n_sum > 1: the M columns are n_sum groups of
+// n_out labels whose absolute values are added (the sum over paddings).
+template <typename T>
+__global__ void label_mix_kernel(const T* __restrict__ signed_ov, int64_t N, int S, const T* __restrict__ V,
+                                 int n_out, int n_sum, T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char mix_smem[];
+  T* Vs = reinterpret_cast<T*>(mix_smem);
+  const int M = n_out * n_sum;
+  for (int i = threadIdx.x; i < S * M; i += blockDim.x) Vs[i] = V[i];
+  __syncthreads();
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N * n_out; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / n_out;
+    const int l = (int)(e % n_out);
+    const T* o = signed_ov + (size_t)i * S;
+    T tot = T(0);
+    for (int p = 0; p < n_sum; ++p) {
+      T acc = T(0);
+      for (int j = 0; j < S; ++j) acc += o[j] * Vs[j * M + p * n_out + l];
+      tot += Num<T>::abs(acc);
+    }
+    out[e] = tot;
+  }
+}
+
+// Ensemble voting on device (variational_mpo_classifiers.py:321-332, 348-363, k = 1):
+// member predictions pred[k][i][0..n_labels) (|overlaps|, row stride S) -> every row normalised to
+// sum 1 (``ensemble_predictions``, written to norm_out when given), their sum over members and its
+// argmax (soft vote), and the label most members rank first (hard vote; ties go to the label whose
+// first voter comes first, as collections.Counter.most_common does).
+template <typename T>
+__global__ void ensemble_vote_kernel(const T* __restrict__ pred, int K, int64_t N, int S, int n_labels,
+                                     T* __restrict__ norm_out, T* __restrict__ soft_out,
+                                     int32_t* __restrict__ soft_argmax, int32_t* __restrict__ hard_argmax) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    T soft[OC_MAX_LABEL];
+    int votes[OC_MAX_LABEL], first[OC_MAX_LABEL];
+#pragma unroll
+    for (int l = 0; l < OC_MAX_LABEL; ++l) {
+      soft[l] = T(0);
+      votes[l] = 0;
+      first[l] = 1 << 30;
+    }
+    for (int k = 0; k < K; ++k) {
+      const T* p = pred + ((size_t)k * N + i) * S;
+      T sum = T(0);
+      for (int l = 0; l < n_labels; ++l) sum += p[l];
+      const T inv = sum > T(0) ? T(1) / sum : T(0);
+      int best = 0;
+      T bv = p[0];
+#pragma unroll
+      for (int l = 0; l < OC_MAX_LABEL; ++l) {
+        if (l < n_labels) {
+          const T v = p[l] * inv;
+          soft[l] += v;
+          if (norm_out) norm_out[((size_t)k * N + i) * n_labels + l] = v;
+          if (p[l] > bv) { bv = p[l]; best = l; }
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < OC_MAX_LABEL; ++l) {
+        if (l == best) {
+          votes[l] += 1;
+          first[l] = first[l] < k ? first[l] : k;
+        }
+      }
+    }
+    int sb = 0, hb = 0, hbv = -1, hbf = 1 << 30;
+    T sbv = T(-1);
+#pragma unroll
+    for (int l = 0; l < OC_MAX_LABEL; ++l) {
+      if (l < n_labels) {
+        if (soft_out) soft_out[(size_t)i * n_labels + l] = soft[l];
+        if (soft[l] > sbv) { sbv = soft[l]; sb = l; }
+        if (votes[l] > hbv || (votes[l] == hbv && first[l] < hbf)) { hbv = votes[l]; hbf = first[l]; hb = l; }
+      }
+    }
+    if (soft_argmax) soft_argmax[i] = sb;
+    if (hard_argmax) hard_argmax[i] = hb;
   }
 }
 

@@ -731,8 +731,8 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       float v = 0.f;
 #pragma unroll
       for (int l = 0; l < 16; ++l) v = lane == l ? acc[l] : v;
+      if (lane < 16) reinterpret_cast<float*>(P.overlaps)[(size_t)img * 16 + lane] = P.signed_out ? v : fabsf(v);
       v = fabsf(v);
-      if (lane < 16) reinterpret_cast<float*>(P.overlaps)[(size_t)img * 16 + lane] = v;
       if (P.argmax) {
         float best = lane < 16 ? v : -1.f;
         int besti = lane;
@@ -829,7 +829,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       for (int j = 0; j < 4; ++j) {
         const float v = fabsf(acc[j]);
         if (lane < 4) {
-          ov[4 * lq + j] = v;
+          ov[4 * lq + j] = P.signed_out ? acc[j] : v;
           if (v > best) { best = v; besti = 4 * lq + j; }
         }
       }
@@ -929,7 +929,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
         const int l = 4 * lq + j;
         const float v = fabsf(acc[j]);
         if (lane < lq_n && l < S) {
-          ov[l] = v;
+          ov[l] = P.signed_out ? acc[j] : v;
           if (v > best) { best = v; besti = l; }
         }
       }
@@ -986,8 +986,8 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
 #pragma unroll
           for (int w2 = 0; w2 < 8; ++w2) v += rb[(size_t)w2 * PER_WARP];
         }
+        if (valid && lane < 16) reinterpret_cast<float*>(P.overlaps)[(size_t)img * 16 + lane] = P.signed_out ? v : fabsf(v);
         v = fabsf(v);
-        if (valid && lane < 16) reinterpret_cast<float*>(P.overlaps)[(size_t)img * 16 + lane] = v;
         if (P.argmax) {
           float best = lane < 16 ? v : -1.f;
           int besti = lane;

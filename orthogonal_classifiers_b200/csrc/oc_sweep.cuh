@@ -64,120 +64,166 @@ struct SweepParams {
   int bonds[OC_MAX_L + 1];
 };
 
-constexpr int kSwLd = 32;                        // row stride of the per-warp square buffers
-constexpr int kSwPerWarp = 2048 + 3 * 1024 + 64; // Bs | C | R1 | R2 | q   (elements of T)
+// Per-image shared-memory block for lane groups of G lanes (G = 8, 16, 32 >= the largest bond):
+// Bs 2 G (G + 1) (dead after the M build: R1 | R2 reuse it) | pad | C G^2 | q 2 G   (elements of T)
+__host__ __device__ constexpr int sw_per_image(int G) { return 3 * G * G + 4 * G; }
 
-// One site with ROWS = 2 * HR register rows per column (HR >= a_m).
+template <typename T, int G>
+__device__ __forceinline__ T group_sum_g(T v) {
+#pragma unroll
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// sum_i a[i] * b[i] with four independent accumulators (a serial chain of ROWS dependent FMAs
+// would cost ROWS x 4 cycles per step with only a few warps per scheduler to hide it)
+// q (ROWS elements, 16-byte aligned shared memory) -> registers with 128-bit loads
 template <typename T, int ROWS>
-__device__ __forceinline__ void qr_site(const T* __restrict__ Ain, T* __restrict__ Aout, int al, int ar, T* Bs,
-                                        T* C, T* R1, T* R2, T* qb, int lane, bool last) {
+__device__ __forceinline__ void load_q(T (&q)[ROWS], const T* __restrict__ qb) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int i = 0; i < ROWS; i += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(qb + i);
+      q[i] = v.x; q[i + 1] = v.y; q[i + 2] = v.z; q[i + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < ROWS; i += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(qb + i);
+      q[i] = v.x; q[i + 1] = v.y;
+    }
+  }
+}
+template <typename T, int ROWS>
+__device__ __forceinline__ void store_q(T* __restrict__ qb, const T (&q)[ROWS]) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int i = 0; i < ROWS; i += 4) *reinterpret_cast<float4*>(qb + i) = make_float4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < ROWS; i += 2) *reinterpret_cast<double2*>(qb + i) = make_double2(q[i], q[i + 1]);
+  }
+}
+
+template <typename T, int ROWS, typename A>
+__device__ __forceinline__ T dot4(const A& a, const T (&b)[ROWS]) {
+  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+#pragma unroll
+  for (int i = 0; i < ROWS; i += 4) {
+    s0 += a[i] * b[i];
+    s1 += a[i + 1] * b[i + 1];
+    s2 += a[i + 2] * b[i + 2];
+    s3 += a[i + 3] * b[i + 3];
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+// One site for every image of the warp (32 / G images, G lanes each, lane = column), with
+// ROWS = 2 * HR register rows per column (HR >= a_m).  Loop bounds are warp-uniform (the bond
+// profile is fixed); what depends on the image (dead columns, rank) is predicated.
+template <typename T, int ROWS, int G>
+__device__ __forceinline__ void qr_site(const T* __restrict__ Ain, T* __restrict__ Aout, bool valid, int al, int ar,
+                                        T* Bs, T* C, T* R1, T* R2, T* qb, int gl, bool last) {
   constexpr int HR = ROWS / 2;
-  // ---- stage B_m[s][l][r] = A'[s][r][l] as Bs[(s * al + l) * 32 + r] ----
-  for (int e = lane; e < 2 * ar * al; e += 32) {
-    const int l = e % al, sr = e / al, r = sr % ar, s = sr / ar;
-    Bs[(s * al + l) * kSwLd + r] = Ain[e];
+  // ---- stage B_m[s][l][r] = A'[s][r][l] as Bs[(s * al + l) * (G + 1) + r]: lane = l, rows of A'
+  //      read contiguously, the odd stride keeps the transposing stores off one bank ----
+  constexpr int LDB = G + 1;
+  if (gl < al) {
+    for (int sr = 0; sr < 2 * ar; ++sr) {
+      const int s = sr >= ar ? 1 : 0, r = sr - s * ar;
+      Bs[(s * al + gl) * LDB + r] = valid ? Ain[sr * al + gl] : T(0);
+    }
   }
   __syncwarp();
-  // ---- M column of this lane: col[s * HR + k] = sum_l C[k][l] B[s][l][lane] ----
+  // ---- M column of this lane: col[s * HR + k] = sum_l C[k][l] B[s][l][gl] ----
   T col[ROWS];
 #pragma unroll
   for (int i = 0; i < ROWS; ++i) col[i] = T(0);
-  const bool mine = lane < ar;
+  const bool mine = gl < ar;
   for (int l = 0; l < al; ++l) {
-    const T b0 = mine ? Bs[l * kSwLd + lane] : T(0);
-    const T b1 = mine ? Bs[(al + l) * kSwLd + lane] : T(0);
+    const T b0 = mine ? Bs[l * LDB + gl] : T(0);
+    const T b1 = mine ? Bs[(al + l) * LDB + gl] : T(0);
 #pragma unroll
     for (int k = 0; k < HR; ++k) {
-      const T c = k < al ? C[k * kSwLd + l] : T(0);
+      const T c = k < al ? C[k * G + l] : T(0);
       col[k] += c * b0;
       col[HR + k] += c * b1;
     }
   }
-  T n2 = T(0);
-#pragma unroll
-  for (int i = 0; i < ROWS; ++i) n2 += col[i] * col[i];
-  const T fro = warp_sum(n2);
+  T n2 = dot4<T, ROWS>(col, col);
+  const T fro = group_sum_g<T, G>(n2);
   const T thr2 = Num<T>::floor_rel() * Num<T>::floor_rel() * fro;
-  // zero-fill R1 / R2 rows this site can touch
-  for (int e = lane; e < ar * kSwLd; e += 32) {
+  __syncwarp();  // every lane is done with Bs: R1 / R2 take its place
+  for (int e = gl; e < ar * G; e += G) {
     R1[e] = T(0);
     R2[e] = T(0);
   }
   __syncwarp();
   // ---- pass 1: MGS in natural column order; live columns take steps 0, 1, ... ----
   int pos = -1;  // step of this lane's column (-1: dead or no column)
-  int nk = 0;
+  int nk = 0;    // live columns so far (same in all lanes of the group)
   for (int t = 0; t < ar; ++t) {
-    const T nt = __shfl_sync(FULL, n2, t);
-    if (!(nt > thr2)) {  // warp-uniform: dead column
-      if (lane == t) {
+    const T nt = __shfl_sync(FULL, n2, t, G);
+    const bool live = nt > thr2;
+    const T inv = live ? Num<T>::rsqrt(nt) : T(0);
+    if (gl == t) {
 #pragma unroll
-        for (int i = 0; i < ROWS; ++i) col[i] = T(0);
+      for (int i = 0; i < ROWS; ++i) col[i] *= inv;  // dead: the column becomes exactly zero
+      store_q<T, ROWS>(qb, col);
+      if (live) {
+        pos = nk;
+        R1[nk * G + t] = nt * inv;
+      } else {
         n2 = T(0);
       }
-      continue;
-    }
-    const T inv = Num<T>::rsqrt(nt);
-    if (lane == t) {
-#pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        col[i] *= inv;
-        qb[i] = col[i];
-      }
-      pos = nk;
-      R1[nk * kSwLd + t] = nt * inv;
     }
     __syncwarp();
-    if (mine && lane > t) {
-      T r = T(0);
+    if (mine && gl > t && live) {
+      T q[ROWS];
+      load_q<T, ROWS>(q, qb);
+      const T r = dot4<T, ROWS>(q, col);
 #pragma unroll
-      for (int i = 0; i < ROWS; ++i) r += qb[i] * col[i];
-      T acc = T(0);
-#pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        col[i] -= r * qb[i];
-        acc += col[i] * col[i];
-      }
-      n2 = acc;
-      R1[nk * kSwLd + lane] = r;
+      for (int i = 0; i < ROWS; ++i) col[i] -= r * q[i];
+      n2 = dot4<T, ROWS>(col, col);
+      R1[nk * G + gl] = r;
     }
     __syncwarp();
-    ++nk;
+    nk += live ? 1 : 0;
   }
   const int rank = nk;
+  const int rank_max = __reduce_max_sync(FULL, rank);
   // ---- pass 2: the same on Q1 (step order), R2[i][step] ----
-  for (int i = 0; i < rank; ++i) {
+  for (int i = 0; i < rank_max; ++i) {
+    const bool on = i < rank;
     const unsigned who = __ballot_sync(FULL, pos == i);
-    const int src = __ffs(who) - 1;
-    T m2 = T(0);
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) & ~(G - 1));
+    const int src = on ? (__ffs(who & gmask) - 1) & (G - 1) : 0;
+    const T m2 = dot4<T, ROWS>(col, col);
+    const T ni = __shfl_sync(FULL, m2, src, G);
+    const T inv = on ? Num<T>::rsqrt(ni) : T(0);
+    if (on && gl == src) {
 #pragma unroll
-    for (int e = 0; e < ROWS; ++e) m2 += col[e] * col[e];
-    const T ni = __shfl_sync(FULL, m2, src);
-    const T inv = Num<T>::rsqrt(ni);
-    if (lane == src) {
-#pragma unroll
-      for (int e = 0; e < ROWS; ++e) {
-        col[e] *= inv;
-        qb[e] = col[e];
-      }
-      R2[i * kSwLd + i] = ni * inv;
+      for (int e = 0; e < ROWS; ++e) col[e] *= inv;
+      store_q<T, ROWS>(qb, col);
+      R2[i * G + i] = ni * inv;
     }
     __syncwarp();
-    if (pos > i) {
-      T r = T(0);
+    if (on && pos > i) {
+      T q[ROWS];
+      load_q<T, ROWS>(q, qb);
+      const T r = dot4<T, ROWS>(q, col);
 #pragma unroll
-      for (int e = 0; e < ROWS; ++e) r += qb[e] * col[e];
-#pragma unroll
-      for (int e = 0; e < ROWS; ++e) col[e] -= r * qb[e];
-      R2[i * kSwLd + pos] = r;
+      for (int e = 0; e < ROWS; ++e) col[e] -= r * q[e];
+      R2[i * G + pos] = r;
     }
     __syncwarp();
   }
   // ---- A_m[(s * al + k) * ar + slot]: live columns at their step, dead ones (zeros) behind ----
   {
-    const unsigned deadmask = __ballot_sync(FULL, mine && pos < 0);
-    const int slot = pos >= 0 ? pos : rank + __popc(deadmask & ((1u << lane) - 1u));
-    if (mine) {
+    const unsigned gsh = (threadIdx.x & 31) & ~(G - 1);
+    const unsigned deadmask = (__ballot_sync(FULL, mine && pos < 0) >> gsh) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+    const int slot = pos >= 0 ? pos : rank + __popc(deadmask & ((1u << gl) - 1u));
+    if (mine && valid) {
 #pragma unroll
       for (int k = 0; k < HR; ++k) {
         if (k < al) {
@@ -192,54 +238,60 @@ __device__ __forceinline__ void qr_site(const T* __restrict__ Ain, T* __restrict
     for (int i = 0; i < ar; ++i) {
       T acc = T(0);
       if (i < rank && mine)
-        for (int t = i; t < rank; ++t) acc += R2[i * kSwLd + t] * R1[t * kSwLd + lane];
-      if (lane < kSwLd) C[i * kSwLd + lane] = acc;
+        for (int t = i; t < rank; ++t) acc += R2[i * G + t] * R1[t * G + gl];
+      C[i * G + gl] = acc;
     }
   }
   __syncwarp();
 }
 
-template <typename T>
+template <typename T, int G>
 __global__ void __launch_bounds__(128) sweep_back_kernel(const __grid_constant__ SweepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int IPW = 32 / G;  // images per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  T* base = reinterpret_cast<T*>(smem_raw) + (size_t)warp * kSwPerWarp;
+  const int gl = lane & (G - 1), grp = lane / G;
+  T* base = reinterpret_cast<T*>(smem_raw) + (size_t)(warp * IPW + grp) * sw_per_image(G);
   T* Bs = base;
-  T* C = base + 2048;
-  T* R1 = C + 1024;
-  T* R2 = R1 + 1024;
-  T* qb = R2 + 1024;
+  T* R1 = base;
+  T* R2 = base + G * G;
+  T* C = base + 2 * G * G + 2 * G;
+  T* qb = C + G * G;
   const int L = P.L;
-  for (int64_t img = (int64_t)blockIdx.x * wpb + warp; img < P.N; img += (int64_t)gridDim.x * wpb) {
-    const T* tin = reinterpret_cast<const T*>(P.tmp_mps) + (size_t)img * P.mps_stride;
-    T* out = reinterpret_cast<T*>(P.mps_out) + (size_t)img * P.mps_stride;
-    if (lane == 0) C[0] = T(1);
+  for (int64_t w0 = (int64_t)blockIdx.x * wpb + warp; w0 * IPW < P.N; w0 += (int64_t)gridDim.x * wpb) {
+    const int64_t img = w0 * IPW + grp;
+    const bool valid = img < P.N;
+    const int64_t im = valid ? img : 0;
+    const T* tin = reinterpret_cast<const T*>(P.tmp_mps) + (size_t)im * P.mps_stride;
+    T* out = reinterpret_cast<T*>(P.mps_out) + (size_t)im * P.mps_stride;
+    if (gl == 0) C[0] = T(1);
     __syncwarp();
     for (int m = 0; m < L; ++m) {
       const int al = P.bonds[m], ar = P.bonds[m + 1];
       const T* Ain = tin + P.site_off[L - 1 - m];
       T* Aout = out + P.site_off[m];
       const bool last = m == L - 1;
-      if (al <= 4) qr_site<T, 8>(Ain, Aout, al, ar, Bs, C, R1, R2, qb, lane, last);
-      else if (al <= 8) qr_site<T, 16>(Ain, Aout, al, ar, Bs, C, R1, R2, qb, lane, last);
-      else if (al <= 16) qr_site<T, 32>(Ain, Aout, al, ar, Bs, C, R1, R2, qb, lane, last);
-      else qr_site<T, 64>(Ain, Aout, al, ar, Bs, C, R1, R2, qb, lane, last);
+      if (al <= 4) qr_site<T, 8, G>(Ain, Aout, valid, al, ar, Bs, C, R1, R2, qb, gl, last);
+      else if (al <= 8) qr_site<T, 16, G>(Ain, Aout, valid, al, ar, Bs, C, R1, R2, qb, gl, last);
+      else if (G > 8 && al <= 16) qr_site<T, (G > 8 ? 32 : 16), G>(Ain, Aout, valid, al, ar, Bs, C, R1, R2, qb, gl, last);
+      else if (G > 16) qr_site<T, (G > 16 ? 64 : 16), G>(Ain, Aout, valid, al, ar, Bs, C, R1, R2, qb, gl, last);
     }
     // singular values / sweep counts the right-to-left sweep saw: row n (bond n + 1) is step
     // L - 2 - n of the mirrored chain; row L - 1 (the norm of the truncated image) stays
-    if (P.sv_out) {
+    if (P.sv_out && valid) {
       const T* si = reinterpret_cast<const T*>(P.tmp_sv) + (size_t)img * L * P.sv_width;
       T* so = reinterpret_cast<T*>(P.sv_out) + (size_t)img * L * P.sv_width;
-      for (int e = lane; e < L * P.sv_width; e += 32) {
+      for (int e = gl; e < L * P.sv_width; e += G) {
         const int n = e / P.sv_width, k = e % P.sv_width;
         const int src = n == L - 1 ? n : L - 2 - n;
         so[e] = si[src * P.sv_width + k];
       }
     }
-    if (P.sw_out && lane < L) {
-      const int src = lane == L - 1 ? lane : L - 2 - lane;
-      P.sw_out[(size_t)img * L + lane] = P.tmp_sw[(size_t)img * L + src];
-    }
+    if (P.sw_out && valid)
+      for (int n = gl; n < L; n += G) {
+        const int src = n == L - 1 ? n : L - 2 - n;
+        P.sw_out[(size_t)img * L + n] = P.tmp_sw[(size_t)img * L + src];
+      }
     __syncwarp();
   }
 }

@@ -72,22 +72,42 @@ def _label_indices(q_hairy_bitstrings, S):
     return idx
 
 
+def _mix_matrix(mpo_classifier, bitstrings):
+    """(hairy site c, V (S, M)): column m = bitstring m's vector on the classifier's hairy site
+    times the product of its (size-1) entries on every other site."""
+    sites = _classifier_sites(mpo_classifier)
+    s_dims = [w.shape[1] for w in sites]
+    c = int(np.argmax(s_dims))
+    cols = []
+    for b in bitstrings:
+        vecs = _bitstring_sites(b, sites)
+        scale = 1.0
+        for n, v in enumerate(vecs):
+            if n != c:
+                if v.size != 1:
+                    raise ValueError("only one classifier site may carry a label leg")
+                scale = scale * v[0]
+        cols.append(scale * vecs[c])
+    return c, np.stack(cols, axis=1)
+
+
 def classifier_predictions(mpo_classifier, mps_test, q_hairy_bitstrings=10):
     """variational_mpo_classifiers.py:309-318 — N x n_labels
     ``abs(<image| classifier |bitstring>)``; one batched contraction instead
-    of N x n_labels quimb contractions."""
+    of N x n_labels quimb contractions.  One-hot label bitstrings (what the reference
+    builds, :39-51) select columns of the overlap kernel's output; arbitrary product
+    bitstrings are contracted on the device from the signed label vectors
+    (``oc_overlap_batch_signed`` + ``oc_label_mix``): two launches for any number of them."""
     batch = _batch_of(mps_test)
     cols = None
     try:
         if not (q_hairy_bitstrings is None or isinstance(q_hairy_bitstrings, int)):
             cols = _label_indices(q_hairy_bitstrings, 0)
     except ValueError:
-        # general product bitstrings: fix the label legs on the host, one launch per bitstring
-        out = []
-        for b in q_hairy_bitstrings:
-            ov, _ = batched.overlaps_from_mps(batch, project_classifier(mpo_classifier, b), return_argmax=False)
-            out.append(ov.double().cpu().numpy()[:, 0])
-        return [list(row) for row in np.stack(out, axis=1)]
+        _, V = _mix_matrix(mpo_classifier, q_hairy_bitstrings)
+        sg, _ = batched.overlaps_from_mps(batch, mpo_classifier, return_argmax=False, signed=True)
+        out = batched.label_mix(sg, V, V.shape[1], 1).double().cpu().numpy()
+        return [list(row) for row in out]
     ov, _ = batched.overlaps_from_mps(batch, mpo_classifier, return_argmax=False)
     ov = ov.double().cpu().numpy()
     if cols is None:
@@ -126,13 +146,52 @@ def project_classifier(mpo_classifier, bitstring):
     return [np.einsum("dsij,s->dij", w, v)[:, None] for w, v in zip(sites, vecs)]
 
 
+class EnsemblePredictions(list):
+    """``ensemble_predictions``' return value: the reference's nested list
+    (member x image x label, rows normalised) that also keeps the votes the device kernel
+    computed alongside, so that the k = 1 evaluators below count on the device."""
+
+    soft_argmax = None   # device int32 (N,)
+    hard_argmax = None   # device int32 (N,)
+
+
 def ensemble_predictions(ensemble, mps_test, q_hairy_bitstrings=10):
     """variational_mpo_classifiers.py:321-332 — classifier_predictions for each
-    member, every image's label vector normalised to sum 1."""
-    out = []
-    for classifier in ensemble:
-        p = np.asarray(classifier_predictions(classifier, mps_test, q_hairy_bitstrings), dtype=np.float64)
-        out.append([row / np.sum(row) for row in p])
+    member, every image's label vector normalised to sum 1.  One overlap launch per
+    member into a (K, N, S) device buffer, then ``oc_ensemble_vote`` normalises the rows
+    and takes the soft / hard votes in the same pass."""
+    import torch
+    batch = _batch_of(mps_test)
+    ensemble = list(ensemble)
+    cols = None
+    if not (q_hairy_bitstrings is None or isinstance(q_hairy_bitstrings, int)):
+        try:
+            cols = _label_indices(q_hairy_bitstrings, 0)
+        except ValueError:
+            cols = False
+    n_labels = q_hairy_bitstrings if isinstance(q_hairy_bitstrings, int) else None
+    if cols is False or (cols is not None and cols != list(range(len(cols)))):
+        # bitstrings that are not "label l -> entry l": per member on the general route
+        out = EnsemblePredictions()
+        for classifier in ensemble:
+            p = np.asarray(classifier_predictions(classifier, mps_test, q_hairy_bitstrings), dtype=np.float64)
+            out.append([row / np.sum(row) for row in p])
+        return out
+    if cols is not None:
+        n_labels = len(cols)
+    clfs = [batched._as_classifier(c, batch.dtype, batch.data.device) for c in ensemble]
+    S = clfs[0].S
+    if any(c.S != S for c in clfs):
+        raise ValueError("ensemble members have different label legs")
+    if n_labels is None:
+        n_labels = S
+    pred = torch.empty((len(clfs), len(batch), S), dtype=batch.data.dtype, device=batch.data.device)
+    for k, c in enumerate(clfs):
+        batched.overlaps_from_mps(batch, c, return_argmax=False, out=pred[k])
+    norm, _, sa, ha = batched.ensemble_vote(pred, n_labels)
+    host = norm.double().cpu().numpy()
+    out = EnsemblePredictions([row for row in member] for member in host)
+    out.soft_argmax, out.hard_argmax = sa, ha
     return out
 
 
@@ -140,19 +199,17 @@ def padded_classifier_predictions(mpo_classifier, mps_test, padded_q_hairy_bitst
     """variational_mpo_classifiers.py:334-337 — for every label, the sum over
     its padding bitstrings of ``abs(<image| classifier |bitstring>)``.
     ``padded_q_hairy_bitstrings[p][l]`` is the bitstring of padding p, label l
-    (np.sum(..., axis=0) in the reference runs over p).  Each (p, l) fixes all
-    label legs, leaving a label-free MPO that is contracted with the whole
-    batch at once."""
+    (np.sum(..., axis=0) in the reference runs over p).  One signed overlap launch for the
+    batch, then ONE ``oc_label_mix`` launch contracts the label leg with all P x n_labels
+    bitstrings and sums the absolute values over the paddings."""
     batch = _batch_of(mps_test)
-    total = None
-    for paddings in padded_q_hairy_bitstrings:
-        cols = []
-        for b in paddings:
-            proj = project_classifier(mpo_classifier, b)
-            ov, _ = batched.overlaps_from_mps(batch, proj, return_argmax=False)
-            cols.append(ov.double().cpu().numpy()[:, 0])
-        block = np.stack(cols, axis=1)
-        total = block if total is None else total + block
+    paddings = [list(p) for p in padded_q_hairy_bitstrings]
+    n_out = len(paddings[0])
+    if any(len(p) != n_out for p in paddings):
+        raise ValueError("every padding needs one bitstring per label")
+    _, V = _mix_matrix(mpo_classifier, [b for p in paddings for b in p])
+    sg, _ = batched.overlaps_from_mps(batch, mpo_classifier, return_argmax=False, signed=True)
+    total = batched.label_mix(sg, V, n_out, len(paddings)).double().cpu().numpy()
     return [row for row in total]
 
 
@@ -163,16 +220,31 @@ def evaluate_classifier_top_k_accuracy(predictions, y_test, k):
     return np.mean([int(i in j) for i, j in zip(y_test, top_k_predictions)])
 
 
+def _device_vote_accuracy(argmax_dev, y_test):
+    import torch
+    lab = torch.as_tensor(np.asarray(y_test).astype(np.uint8)).to(argmax_dev.device)
+    c = batched.count_correct(argmax_dev, lab).cpu()
+    return float(c[0].item()) / max(1, int(c[1].item()))
+
+
 def evaluate_soft_ensemble_top_k_accuracy(e_predictions, y_test, k):
-    """variational_mpo_classifiers.py:348-354 (verbatim semantics)."""
+    """variational_mpo_classifiers.py:348-354.  k = 1 on what ``ensemble_predictions``
+    returned: the votes were taken on the device, only the count remains
+    (``oc_count_correct``); otherwise the reference's host arithmetic."""
+    if k == 1 and isinstance(e_predictions, EnsemblePredictions) and e_predictions.soft_argmax is not None \
+            and len(y_test) == e_predictions.soft_argmax.numel():
+        return _device_vote_accuracy(e_predictions.soft_argmax, y_test)
     top_k_ensemble_predictions = np.sum(e_predictions, axis=0)
     top_k_predictions = [np.argpartition(p, -k)[-k:] for p in top_k_ensemble_predictions]
     return np.mean([int(i in j) for i, j in zip(y_test, top_k_predictions)])
 
 
 def evaluate_hard_ensemble_top_k_accuracy(e_predictions, y_test, k):
-    """variational_mpo_classifiers.py:356-363 (verbatim semantics: every member
-    votes with its top-k labels, the k most common win)."""
+    """variational_mpo_classifiers.py:356-363 (every member votes with its top-k labels, the
+    k most common win).  k = 1 on ``ensemble_predictions``' result: device votes, as above."""
+    if k == 1 and isinstance(e_predictions, EnsemblePredictions) and e_predictions.hard_argmax is not None \
+            and len(y_test) == e_predictions.hard_argmax.numel():
+        return _device_vote_accuracy(e_predictions.hard_argmax, y_test)
     from collections import Counter
     votes = np.array([[np.argpartition(p, -k)[-k:] for p in member] for member in e_predictions])
     votes = votes.transpose(1, 0, 2).reshape(len(y_test), -1)

@@ -1,10 +1,6 @@
 #!/bin/bash
-# end-to-end throughput for several H2D/compute pipeline chunk sizes
-for c in ${CHUNKS:-8750 17500 23334 35000 70000}; do
-  python bench.py --no-cpu-baseline --e2e-chunk $c 2>/dev/null | tail -1 > /tmp/b.json
-  python - "$c" <<'P'
-import json, sys
-d = json.load(open('/tmp/b.json'))
-print(sys.argv[1], 'device', round(d['value'] / 1e6, 2), 'e2e f32', round(d['e2e']['value'] / 1e6, 2), 'e2e u8', round(d['e2e_u8']['value'] / 1e6, 2))
-P
+# oc_classify_host chunk schedule: e2e (uint8) and e2e_f32 for a few stage sizes
+for c in 8750 11667 17500 23334 35000 70000; do
+  python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-config5 --e2e-chunk $c 2>/dev/null | tail -1 | \
+    python -c "import sys,json; d=json.loads(sys.stdin.read()); print($c, 'u8 %.3f ms  f32 %.3f ms' % (d['e2e']['ms_per_step'], d['e2e_f32']['ms_per_step']))"
 done

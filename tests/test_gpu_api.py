@@ -205,3 +205,95 @@ def test_classifier_cache_follows_content_changes(gpu_lib):
                           for i in range(len(imgs))])
         assert np.abs(ov10 - ref10).max() <= 1e-5 * ref10.max()
         del clf
+
+
+def test_stacking_matches_reference_fixture(gpu_lib):
+    """experiments.py:528-640 (BASELINE config 4): label 16-vectors -> L = 4 MPS
+    (``mps_encoding(v, None)``) -> product of n + 1 copies -> overlap with the stacking
+    unitary, L = 4 (n + 1) <= 16, label leg on the centre site.  Fixture: the reference's own
+    ``mps_stacking`` (tests/golden/generate_golden_stacking.py) — its stacking unitary, stacked
+    predictions and accuracy for n = 0..3."""
+    from orthogonal_classifiers_b200 import experiments as ex
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_stacking.npz"))
+    for dtype in ("f32", "f64"):
+        mps = gpu_lib.mps_encoding(g["v_test"], None, dtype=dtype)
+        assert mps.batch.L == 4 and mps.batch.bonds == [1, 2, 4, 2, 1]
+        for n in range(4):
+            L = 4 * (n + 1)
+            unitary = [g[f"unitary_{n}_site_{i}"] for i in range(L)]
+            assert int(np.argmax([w.shape[1] for w in unitary])) == L // 2
+            copies = ex.generate_copy_state(mps, n)
+            assert copies.L == L and len(copies) == len(g["v_test"])
+            # the copy state is the n + 1-fold tensor power of the normalised vector
+            st = oracle.mps_to_state([s.astype(np.float64) for s in copies.sites_numpy(3)])
+            v = g["v_test"][3] / np.linalg.norm(g["v_test"][3])
+            ref_st = v
+            for _ in range(n):
+                ref_st = np.kron(ref_st, v)
+            assert min(np.abs(st - ref_st).max(), np.abs(st + ref_st).max()) < 10 * TOL[dtype]
+            pred = ex.stacked_predictions(mps, unitary, n)
+            ref = g[f"pred_{n}"]
+            assert pred.shape == ref.shape
+            assert np.abs(pred - ref).max() <= TOL[dtype] * ref.max(), (dtype, n)
+            assert ex.evaluate_stacking(mps, unitary, n, g["y_test"]) == float(g[f"acc_{n}"])
+
+
+def test_prediction_arrays_and_files(gpu_lib, golden, tmp_path):
+    """experiments.py:332-352: the (n_D, N, 16) arrays and the files the plotting scripts read."""
+    from conftest import golden_sites
+    from orthogonal_classifiers_b200 import experiments as ex
+    names = ["e32_b32_f32_nonortho", "e32_b32_f32_ortho", "e32_b8_f8_ortho"]
+    clfs = [golden_sites(golden, f"clf_{n}") for n in names]
+    mps = gpu_lib.mps_encoding(golden["x_test"], 32)
+    arr = ex.prediction_array(mps, clfs)
+    assert arr.shape == (3, 16, 16) and arr.dtype == np.float64
+    for k, n in enumerate(names):
+        assert np.abs(arr[k] - golden[f"pred_{n}"]).max() <= 1e-5 * golden[f"pred_{n}"].max()
+    np.testing.assert_array_equal(ex.prediction_array(golden["x_test"], clfs, 32), arr)
+    paths = ex.save_prediction_arrays(str(tmp_path), ortho=arr[1:], non_ortho=arr[:1], kind="test")
+    assert sorted(os.path.basename(p) for p in paths) == ["non_ortho_d_final_vs_test_predictions.npy",
+                                                          "ortho_d_final_vs_test_predictions.npy"]
+    np.testing.assert_array_equal(np.load(tmp_path / "ortho_d_final_vs_test_predictions.npy"), arr[1:])
+    paths = ex.save_prediction_arrays(str(tmp_path), ortho=arr, kind="training")
+    assert os.path.basename(paths[0]) == "ortho_d_final_vs_training_predictions_compressed.npz"
+    np.testing.assert_array_equal(np.load(paths[0])["arr_0"], arr)      # experiments.py:657 reads arr_0
+    np.testing.assert_array_equal(ex.load_prediction_array(paths[0]), arr)
+
+
+def test_ensemble_votes_on_device(gpu_lib):
+    """oc_ensemble_vote / oc_label_mix against the reference's host arithmetic
+    (variational_mpo_classifiers.py:321-363 restated in numpy), ties included."""
+    import torch
+    from collections import Counter
+    from orthogonal_classifiers_b200 import batched
+    rng = np.random.default_rng(3)
+    K, N, S, nl = 5, 3001, 16, 10
+    pred = rng.random((K, N, S))
+    y = rng.integers(0, nl, N)
+    pred[:, np.arange(N), y] += 0.3
+    # exact vote ties: every member of the first 200 images votes for a different label
+    for i in range(200):
+        for k in range(K):
+            pred[k, i, :nl] = 0.01
+            pred[k, i, (i + 2 * k) % nl] = 1.0
+    for dtype, tdt in (("f64", torch.float64), ("f32", torch.float32)):
+        p = pred.astype(np.float64 if dtype == "f64" else np.float32)
+        norm, soft, sa, ha = batched.ensemble_vote(torch.from_numpy(p).cuda(), nl)
+        p64 = p.astype(np.float64)
+        ref_norm = p64[:, :, :nl] / p64[:, :, :nl].sum(2, keepdims=True)
+        tol = 1e-12 if dtype == "f64" else 1e-6
+        assert np.abs(norm.double().cpu().numpy() - ref_norm).max() < tol
+        ref_soft = ref_norm.sum(0)
+        assert np.abs(soft.double().cpu().numpy() - ref_soft).max() < K * tol
+        srt = np.sort(ref_soft, axis=1)
+        clear = (srt[:, -1] - srt[:, -2]) > 1e-5
+        assert np.all((sa.cpu().numpy() == ref_soft.argmax(1)) | ~clear)
+        votes = p64[:, :, :nl].argmax(2).T                              # (N, K)
+        ref_hard = np.array([Counter(v.tolist()).most_common(1)[0][0] for v in votes])
+        np.testing.assert_array_equal(ha.cpu().numpy(), ref_hard)
+    # label mixing: random product bitstrings, two paddings
+    sg = rng.standard_normal((N, S))
+    V = rng.standard_normal((S, 2 * nl))
+    out = batched.label_mix(torch.from_numpy(sg).cuda(), V, nl, 2).cpu().numpy()
+    ref = np.abs(sg @ V[:, :nl]) + np.abs(sg @ V[:, nl:])
+    assert np.abs(out - ref).max() < 1e-12 * np.abs(ref).max()

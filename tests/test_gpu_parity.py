@@ -526,9 +526,13 @@ def test_ensemble_and_padded_predictions_match_reference(gpu_lib, golden):
     ref = ge["e_pred"]
     assert e.shape == ref.shape
     assert np.abs(e - ref).max() < 2e-5 * ref.max()
+    e_list = oc.ensemble_predictions(ensemble, mps_test, 10)   # carries the device votes (k = 1)
+    assert e_list.soft_argmax is not None
     for k in (1, 3):
         assert oc.evaluate_soft_ensemble_top_k_accuracy(e, golden["y_test"], k) == float(ge[f"soft_k{k}"])
         assert oc.evaluate_hard_ensemble_top_k_accuracy(e, golden["y_test"], k) == float(ge[f"hard_k{k}"])
+        assert oc.evaluate_soft_ensemble_top_k_accuracy(e_list, golden["y_test"], k) == float(ge[f"soft_k{k}"])
+        assert oc.evaluate_hard_ensemble_top_k_accuracy(e_list, golden["y_test"], k) == float(ge[f"hard_k{k}"])
     # padded: explicit product bitstrings (second padding scaled by 0.5 on the hairy site)
     L, c = 10, 5
     def bits(label, scale):
