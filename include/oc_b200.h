@@ -182,6 +182,34 @@ int oc_encode_classify(const void* images_dev, int in_dtype, int64_t N,
                        void* workspace_dev, void* overlaps_out_dev,
                        int32_t* argmax_out_dev, void* stream);
 
+/* ---- classifier construction ("batch adding"), fp64 on the device ----
+ *
+ * Replaces deterministic_mpo_classifier.py:21-42 (class_encode_mps_to_mpo / mpo_encoding)
+ * for the reference's one-hot label bitstrings: MPO site n = MPS site n (label leg 1),
+ * site c = A_c (x) e_label (label leg S).
+ *   mps_dev        N image blocks, sites (2, a_n, a_{n+1}) concatenated (oc_encode_batch
+ *                  output), OC_F32 or OC_F64
+ *   labels_dev     N uint8 class labels
+ *   mpos_out_dev   N blocks of sum_n 2 s_n a_n a_{n+1} doubles, s_c = S, s_n = 1 elsewhere */
+int oc_class_encode(const void* mps_dev, int mps_dtype, int64_t N, int L,
+                    const int32_t* mps_bonds_host, const uint8_t* labels_dev, int c, int S,
+                    double* mpos_out_dev, void* stream);
+
+/* Replaces fMPO.add + fMPO.compress_centre_one_site (+ scipy polar) — fMPO.py:666-689,
+ * 338-453 — as adding_centre_batches / add_centre_sublist drive them
+ * (experiments.py:497-523): groups of `batch` consecutive MPOs (the last may be shorter)
+ * are summed and compressed to bond D around the hairy centre site c; `orthogonalise`
+ * replaces the centre tensor by its polar factor, otherwise it is normalised.
+ *   mpos_dev        n_mpos MPOs in one fixed zero-padded shape: sites (2, s_n, b_n, b_{n+1})
+ *                   concatenated, bonds bonds_in_host[L+1] <= 32, s_c = S
+ *   D               <= 0: the reference's D = None (numerical rank only)
+ *   out_dev         ceil(n_mpos / batch) MPOs in the shape bonds_out_host describes;
+ *                   NULL = only fill bonds_out_host (shape query)
+ *   bonds_out_host  out: min(2 x previous, batch x input bond, D) from both edges */
+int oc_add_compress_centre(const double* mpos_dev, int64_t n_mpos, int L, int c, int S,
+                           const int32_t* bonds_in_host, int batch, int D, int orthogonalise,
+                           double* out_dev, int32_t* bonds_out_host, void* stream);
+
 /* Optional: declare the packed classifier at clf_dev immutable (enable = 1) so that
  * oc_overlap_batch / oc_encode_classify on this stream re-lay it for the kernel once
  * instead of on every call; enable = 1 again after changing its contents, enable = 0

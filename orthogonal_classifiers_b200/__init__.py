@@ -8,6 +8,7 @@ from ._lib import OcError  # noqa: F401
 from .batched import (  # noqa: F401
     DeviceClassifier,
     HostPipeline,
+    MPOBatch,
     MPSBatch,
     classify,
     classify_host,
@@ -16,6 +17,11 @@ from .batched import (  # noqa: F401
     evaluate,
     label_overlaps,
     set_force_generic,
+)
+from .deterministic_mpo_classifier import (  # noqa: F401
+    adding_centre_batches,
+    mpo_encoding,
+    prepare_centred_batched_classifier,
 )
 from .distributed import all_reduce_counts, shard_bounds  # noqa: F401
 from .fMPO import fMPO  # noqa: F401

@@ -19,6 +19,7 @@ EXPORTS = [
     "oc_encode_batch", "oc_overlap_batch", "oc_encode_classify", "oc_count_correct",
     "oc_pack_classifier", "oc_classify_host", "oc_fma_peak_launch", "oc_encode_step_ms",
     "oc_classifier_cache", "oc_release", "oc_overlap_batch_signed", "oc_label_mix", "oc_ensemble_vote",
+    "oc_class_encode", "oc_add_compress_centre",
 ]
 
 
@@ -52,6 +53,8 @@ def _load():
     lib.oc_overlap_batch_signed.argtypes = [vp, p32, vp, p32, p32, i32, i64, i32, vp, vp, vp]
     lib.oc_label_mix.argtypes = [vp, i64, i32, vp, i32, i32, i32, vp, vp]
     lib.oc_ensemble_vote.argtypes = [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.oc_class_encode.argtypes = [vp, i32, i64, i32, p32, vp, i32, i32, vp, vp]
+    lib.oc_add_compress_centre.argtypes = [vp, i64, i32, i32, i32, p32, i32, i32, i32, vp, p32, vp]
     lib.oc_classifier_cache.argtypes = [vp, i32, vp]
     lib.oc_release.argtypes = [vp]
     lib.oc_fma_peak_launch.argtypes = [i64, vp, C.POINTER(C.c_double), vp]

@@ -482,3 +482,85 @@ def evaluate(images, labels, classifier, D_encode: int | None = 32, dtype: str =
         all_reduce_counts(counts)
     c = counts.cpu()
     return float(c[0].item()) / max(1, int(c[1].item()))
+
+
+# --------------------------------------------------------------------------
+# classifier construction ("batch adding") on the device, fp64
+# --------------------------------------------------------------------------
+
+class MPOBatch:
+    """n one-hairy-site MPOs of one fixed zero-padded shape on the device (fp64): what the
+    reference holds as a list of ``fMPO`` (fMPO.py:21-51).  ``batch[i]`` is an ``fMPO`` whose
+    ``.data`` are host arrays (d, s, i, j)."""
+
+    def __init__(self, data: torch.Tensor, bonds, L: int, c: int, S: int):
+        self.data, self.bonds, self.L, self.c, self.S = data, [int(b) for b in bonds], int(L), int(c), int(S)
+        self.s = [S if n == c else 1 for n in range(L)]
+        offs = [0]
+        for n in range(L):
+            offs.append(offs[-1] + 2 * self.s[n] * self.bonds[n] * self.bonds[n + 1])
+        self.offsets = offs
+        if data.shape[1] != offs[-1]:
+            raise ValueError(f"MPO block of {data.shape[1]} elements, bonds say {offs[-1]}")
+
+    def __len__(self) -> int:
+        return self.data.shape[0]
+
+    def sites_numpy(self, i: int) -> list:
+        row = self.data[i].cpu().numpy()
+        return [row[self.offsets[n]:self.offsets[n + 1]].reshape(2, self.s[n], self.bonds[n], self.bonds[n + 1]).copy()
+                for n in range(self.L)]
+
+    def __getitem__(self, i):
+        from .fMPO import fMPO
+        if isinstance(i, slice):
+            return MPOBatch(self.data[i], self.bonds, self.L, self.c, self.S)
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return fMPO(self.sites_numpy(i))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def class_encode(mps: MPSBatch, labels, centre: int | None = None, S: int = 16) -> MPOBatch:
+    """deterministic_mpo_classifier.py:21-42 ``mpo_encoding`` for one-hot label bitstrings:
+    image MPS x label -> one-hairy-site MPO (``oc_class_encode``)."""
+    c = mps.L // 2 if centre is None else int(centre)
+    N = len(mps)
+    lab = torch.as_tensor(np.asarray(labels).astype(np.uint8)).to(mps.data.device)
+    if lab.numel() != N:
+        raise ValueError("one label per image")
+    if N and int(lab.max()) >= S:
+        raise ValueError("label does not fit the label leg")
+    csz = 2 * mps.bonds[c] * mps.bonds[c + 1]
+    out = torch.empty((N, mps.offsets[-1] + csz * (S - 1)), dtype=torch.float64, device=mps.data.device)
+    with torch.cuda.device(mps.data.device):
+        check(lib.oc_class_encode(mps.data.data_ptr(), _OC_DT[mps.dtype], N, mps.L, i32_array(mps.bonds),
+                                  lab.data_ptr(), c, S, out.data_ptr(), _stream_ptr()))
+    return MPOBatch(out, mps.bonds, mps.L, c, S)
+
+
+def add_compress_centre(mpos: MPOBatch, D: int | None, batch_num: int, orthogonalise: bool = False) -> MPOBatch:
+    """``adding_centre_batches`` (experiments.py:497-523): every ``batch_num`` consecutive MPOs are
+    summed (fMPO.add) and compressed around the centre site to bond D
+    (fMPO.compress_centre_one_site, polar factor when ``orthogonalise``) by ONE kernel launch
+    (``oc_add_compress_centre``), one CTA per group."""
+    n = len(mpos)
+    bonds_out = (C.c_int32 * (mpos.L + 1))()
+    Dv = 0 if D is None else int(D)
+    check(lib.oc_add_compress_centre(None, n, mpos.L, mpos.c, mpos.S, i32_array(mpos.bonds), int(batch_num), Dv,
+                                     int(bool(orthogonalise)), None, bonds_out, None))
+    bo = list(bonds_out)
+    s = mpos.s
+    elems = sum(2 * s[k] * bo[k] * bo[k + 1] for k in range(mpos.L))
+    n_groups = (n + batch_num - 1) // batch_num
+    out = torch.empty((n_groups, elems), dtype=torch.float64, device=mpos.data.device)
+    data = mpos.data if mpos.data.is_contiguous() else mpos.data.contiguous()
+    with torch.cuda.device(mpos.data.device):
+        check(lib.oc_add_compress_centre(data.data_ptr(), n, mpos.L, mpos.c, mpos.S, i32_array(mpos.bonds),
+                                         int(batch_num), Dv, int(bool(orthogonalise)), out.data_ptr(), bonds_out,
+                                         _stream_ptr()))
+    return MPOBatch(out, bo, mpos.L, mpos.c, mpos.S)

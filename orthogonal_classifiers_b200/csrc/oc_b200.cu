@@ -29,6 +29,7 @@
 #include "oc_encode_gram.cuh"
 #include "oc_overlap_fast.cuh"
 #include "oc_sweep.cuh"
+#include "oc_mpo_build.cuh"
 
 namespace {
 
@@ -119,7 +120,7 @@ struct Ctx {
   std::mutex mu;
   int device = 0;
   cudaStream_t stream = nullptr;
-  Scratch mps, enc_ws, ov_ws, sw_img, sw_mps, sw_sv, sw_sw;
+  Scratch mps, enc_ws, ov_ws, sw_img, sw_mps, sw_sv, sw_sw, build_ws;
   oc::SplitStreams split;
   std::vector<ClfEntry> cache;
   HostPipe hp;
@@ -146,7 +147,7 @@ Ctx& get_ctx(cudaStream_t st) {
 
 void release_ctx(Ctx& cx) {
   cudaStream_t st = cx.stream;
-  for (Scratch* s : {&cx.mps, &cx.enc_ws, &cx.ov_ws, &cx.sw_img, &cx.sw_mps, &cx.sw_sv, &cx.sw_sw}) s->release(st);
+  for (Scratch* s : {&cx.mps, &cx.enc_ws, &cx.ov_ws, &cx.sw_img, &cx.sw_mps, &cx.sw_sv, &cx.sw_sw, &cx.build_ws}) s->release(st);
   for (auto& e : cx.cache) e.prepared.release(st);
   cx.cache.clear();
   HostPipe& hp = cx.hp;
@@ -631,6 +632,103 @@ int oc_encode_classify(const void* images_dev, int in_dtype, int64_t N, int n_pi
     return rc;
   return overlap_impl(cx, ws, bonds, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype, overlaps_out_dev,
                       argmax_out_dev, st);
+}
+
+int oc_class_encode(const void* mps_dev, int mps_dtype, int64_t N, int L, const int32_t* mps_bonds_host,
+                    const uint8_t* labels_dev, int c, int S, double* mpos_out_dev, void* stream) {
+  if (N < 0) return fail(OC_E_ARG, "N < 0");
+  if (L < 1 || L > OC_MAX_SITES || c < 0 || c >= L) return fail(OC_E_ARG, "bad L=%d / c=%d", L, c);
+  if (S < 1 || S > OC_MAX_LABEL) return fail(OC_E_ARG, "label leg %d outside [1,%d]", S, OC_MAX_LABEL);
+  if (mps_dtype != OC_F32 && mps_dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", mps_dtype);
+  if (N == 0) return OC_OK;
+  if (!mps_dev || !mps_bonds_host || !labels_dev || !mpos_out_dev) return fail(OC_E_ARG, "null pointer argument");
+  int64_t off = 0, c_lo = 0, c_hi = 0;
+  for (int n = 0; n < L; ++n) {
+    if (mps_bonds_host[n] < 1 || mps_bonds_host[n + 1] < 1) return fail(OC_E_ARG, "bond %d < 1", n);
+    if (n == c) c_lo = off;
+    off += 2LL * mps_bonds_host[n] * mps_bonds_host[n + 1];
+    if (n == c) c_hi = off;
+  }
+  const int64_t out_stride = off + (c_hi - c_lo) * (S - 1);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (int)std::min<int64_t>(N, (int64_t)num_sms() * 16);
+  if (mps_dtype == OC_F32)
+    oc::build::class_encode_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(mps_dev), off, labels_dev, N,
+                                                               S, (int)c_lo, (int)c_hi, mpos_out_dev, out_stride);
+  else
+    oc::build::class_encode_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(mps_dev), off, labels_dev,
+                                                                N, S, (int)c_lo, (int)c_hi, mpos_out_dev, out_stride);
+  OC_CUDA(cudaGetLastError());
+  return OC_OK;
+}
+
+int oc_add_compress_centre(const double* mpos_dev, int64_t n_mpos, int L, int c, int S, const int32_t* bonds_in_host,
+                           int batch, int D, int orthogonalise, double* out_dev, int32_t* bonds_out_host,
+                           void* stream) {
+  if (n_mpos < 0 || batch < 1) return fail(OC_E_ARG, "bad n_mpos / batch");
+  if (L < 2 || L > OC_MAX_SITES || c < 0 || c >= L) return fail(OC_E_ARG, "bad L=%d / c=%d", L, c);
+  if (S < 1 || S > OC_MAX_LABEL) return fail(OC_E_ARG, "label leg %d outside [1,%d]", S, OC_MAX_LABEL);
+  if (!bonds_in_host || !bonds_out_host) return fail(OC_E_ARG, "null bonds pointer");
+  if (bonds_in_host[0] != 1 || bonds_in_host[L] != 1) return fail(OC_E_ARG, "edge bonds must be 1");
+  oc::build::BuildParams P;
+  memset(&P, 0, sizeof(P));
+  const int Dcap = D > 0 ? std::min(D, oc::build::kR) : oc::build::kR;
+  int bimax = 1;
+  for (int n = 0; n <= L; ++n) {
+    if (bonds_in_host[n] < 1 || bonds_in_host[n] > oc::build::kR)
+      return fail(OC_E_ARG, "input bond %d = %d outside [1,%d]", n, bonds_in_host[n], oc::build::kR);
+    P.bi[n] = bonds_in_host[n];
+    bimax = std::max(bimax, P.bi[n]);
+  }
+  // ranks the sweeps can reach: doubling from the edges, the summed bonds, D (fMPO.py:382-399)
+  P.bo[0] = 1;
+  for (int n = 0; n < c; ++n) P.bo[n + 1] = (int)std::min<int64_t>(std::min<int64_t>(2LL * P.bo[n], (int64_t)batch * P.bi[n + 1]), Dcap);
+  P.bo[L] = 1;
+  for (int n = L - 1; n > c; --n) P.bo[n] = (int)std::min<int64_t>(std::min<int64_t>(2LL * P.bo[n + 1], (int64_t)batch * P.bi[n]), Dcap);
+  if (D <= 0) {
+    // D = None truncates to the numerical rank only; a rank above 32 cannot be represented here
+    for (int n = 1; n < L; ++n)
+      if (P.bo[n] == oc::build::kR && std::min<int64_t>((int64_t)batch * P.bi[n], n <= c ? (n < 31 ? (1LL << n) : (1LL << 31)) : (L - n < 31 ? (1LL << (L - n)) : (1LL << 31))) > oc::build::kR)
+        return fail(OC_E_ARG, "D=None: bond %d may exceed %d", n, oc::build::kR);
+  }
+  int64_t io = 0, oo = 0;
+  for (int n = 0; n <= L; ++n) {
+    bonds_out_host[n] = P.bo[n];
+    P.in_off[n] = io;
+    P.out_off[n] = oo;
+    if (n < L) {
+      const int sn = n == c ? S : 1;
+      io += 2LL * sn * P.bi[n] * P.bi[n + 1];
+      oo += 2LL * sn * P.bo[n] * P.bo[n + 1];
+    }
+  }
+  P.in_stride = io;
+  P.out_stride = oo;
+  if (!out_dev) return OC_OK;  // shape query
+  if (n_mpos == 0) return OC_OK;
+  if (!mpos_dev) return fail(OC_E_ARG, "null input pointer");
+  P.in = mpos_dev;
+  P.out = out_dev;
+  P.n_mpos = n_mpos;
+  P.batch = batch;
+  P.n_groups = (int)((n_mpos + batch - 1) / batch);
+  P.L = L;
+  P.c = c;
+  P.S = S;
+  P.D = D;
+  P.ortho = orthogonalise != 0;
+  P.Jmax = batch * bimax;
+  P.ws_stride = oc::build::ws_doubles(P.Jmax, S);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Ctx& cx = get_ctx(st);
+  std::lock_guard<std::mutex> lk(cx.mu);
+  const int grid = std::min(P.n_groups, num_sms());
+  if (int rc = cx.build_ws.ensure((size_t)grid * P.ws_stride * sizeof(double), st)) return rc;
+  P.ws = reinterpret_cast<double*>(cx.build_ws.p);
+  if (int rc = set_smem(oc::build::add_compress_centre_kernel, oc::build::smem_bytes())) return rc;
+  oc::build::add_compress_centre_kernel<<<grid, oc::build::kThreads, oc::build::smem_bytes(), st>>>(P);
+  OC_CUDA(cudaGetLastError());
+  return OC_OK;
 }
 
 int oc_classifier_cache(const void* clf_dev, int enable, void* stream) {

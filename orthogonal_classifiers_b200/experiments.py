@@ -6,7 +6,8 @@
 * MPS stacking: ``generate_copy_state`` and the stacked predictions
   (experiments.py:528-546, 631-636).
 
-Classifier construction (``adding_centre_batches`` ...) is in ``deterministic.py``.
+Classifier construction (``adding_centre_batches`` ...) is in ``deterministic_mpo_classifier.py``;
+``mps_stacking`` here runs the whole stacking experiment on the device.
 """
 from __future__ import annotations
 
@@ -113,3 +114,22 @@ def evaluate_stacking(test_mps_predictions, stacking_unitary, n_copies: int, y_t
     """experiments.py:631-643: accuracy of the stacked predictions."""
     return evaluate_classifier_top_k_accuracy(stacked_predictions(test_mps_predictions, stacking_unitary, n_copies),
                                               y_test, 1)
+
+
+def mps_stacking(training_mps_predictions, test_mps_predictions, n_copies, y_train, y_test,
+                 D_batch=32, batch_nums=(4, 8, 13, 13), D_final=32, batch_final=10, ortho_at_end=True,
+                 return_details=False):
+    """experiments.py:528-643, end to end on the device: copy states of the training label
+    vectors -> class-encoded MPOs -> batch-added sum states (``prepare_centred_batched_classifier``,
+    D_batch, batch_nums) -> stacking unitary (``adding_centre_batches`` at D_final, polar factor
+    when ``ortho_at_end``) -> overlaps of the test copy states with it -> top-1 accuracy.
+    The defaults are the reference's hard-coded parameters (experiments.py:596-610)."""
+    from .deterministic_mpo_classifier import adding_centre_batches, prepare_centred_batched_classifier
+    train_copies = generate_copy_state(training_mps_predictions, n_copies)
+    sum_states = prepare_centred_batched_classifier(train_copies, y_train, None, D_batch, list(batch_nums))
+    stacking_unitary = adding_centre_batches(sum_states, D_final, batch_final, orthogonalise=ortho_at_end)[0]
+    preds = stacked_predictions(test_mps_predictions, stacking_unitary.data, n_copies)
+    result = evaluate_classifier_top_k_accuracy(preds, y_test, 1)
+    if return_details:
+        return result, preds, stacking_unitary
+    return result

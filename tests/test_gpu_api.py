@@ -297,3 +297,123 @@ def test_ensemble_votes_on_device(gpu_lib):
     out = batched.label_mix(torch.from_numpy(sg).cuda(), V, nl, 2).cpu().numpy()
     ref = np.abs(sg @ V[:, :nl]) + np.abs(sg @ V[:, nl:])
     assert np.abs(out - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+def _left_cut_singular_values(mpos, D, c=5):
+    """Singular values the left sweep of compress_centre_one_site (fMPO.py:400-421) sees at each
+    site of the sum of ``mpos`` (oracle restatement), to tell clean cuts from degenerate ones."""
+    data = oracle.mpo_oracle._add_all(mpos)
+    out = []
+    for m in range(c):
+        d, s, i, j = data[m].shape
+        U, S, Vt = np.linalg.svd(np.asarray(data[m]).real.transpose(0, 2, 1, 3).reshape(d * i, s * j), full_matrices=False)
+        r = min(D, int(np.sum(S > S[0] * 1e-13)))
+        out.append(S)
+        SV = S[:r, None] * Vt[:r]
+        data[m + 1] = np.einsum("rk,dskj->dsrj", SV, np.asarray(data[m + 1]).real)   # s = 1 left of the centre
+    return out
+
+
+@pytest.mark.parametrize("tag", ["e32_b32_f32", "e10_b10_f32", "e32_b8_f8"])
+@pytest.mark.parametrize("ortho", [False, True])
+def test_classifier_construction_on_device(gpu_lib, golden, tag, ortho):
+    """fMPO.add + compress_centre_one_site (+ polar) on the device (fMPO.py:338-453, 666-689;
+    experiments.py:482-523) against the classifiers the reference's own code built
+    (tests/golden/generate_golden.py): the dense operator of the non-orthogonalised ones up to a
+    global sign, the overlaps on the training span for the orthogonalised ones (the polar factor
+    of the rank-deficient centre matrix is unique only there, in the reference too).
+
+    ``e32_b8_f8`` cannot be compared value by value: its D_batch = 8 cut falls INSIDE a block of
+    exactly equal singular values (the summands are isometries, so the summed site matrix has
+    singular values sqrt(5), 2, sqrt(3), ... with high multiplicity), where the subspace an SVD
+    keeps is whatever LAPACK returns — in the reference too.  The test shows the tie and checks
+    what is defined: shapes, isometric sites, unit norm / partial isometry."""
+    from conftest import golden_sites
+    D_encode, D_batch, D_final = [int(t[1:]) for t in tag.split("_")]
+    x, y = golden["x_train"], golden["y_train"]
+    mps = gpu_lib.mps_encoding(x, D_encode, dtype="f64")
+    sums = gpu_lib.prepare_centred_batched_classifier(mps, y, None, D_batch, [8])
+    assert len(sums) == 10
+    clf = gpu_lib.adding_centre_batches(sums, D_final, 10, orthogonalise=ortho)[0]
+    ref = golden_sites(golden, f"clf_{tag}_{'ortho' if ortho else 'nonortho'}")
+    assert [w.shape for w in clf.data] == [w.shape for w in ref]
+    Wg, Wr = oracle.dense_classifier(clf.data), oracle.dense_classifier(ref)
+    for n, w in enumerate(clf.data):          # canonical around the centre
+        if n < 5:
+            M = w[:, 0].reshape(-1, w.shape[3])
+            G = M.T @ M
+        elif n > 5:
+            M = w[:, 0].transpose(1, 0, 2).reshape(w.shape[2], -1)
+            G = M @ M.T
+        else:
+            continue
+        nz = np.diag(G) > 0.5
+        assert np.abs(G[np.ix_(nz, nz)] - np.eye(nz.sum())).max() < 1e-10 and np.abs(G[~nz]).max(initial=0) < 1e-10
+    c = clf.data[5]
+    Mc = c.transpose(0, 2, 1, 3).reshape(c.shape[0] * c.shape[2], -1)
+    if ortho:
+        G = Mc @ Mc.T                          # partial isometry: M M^T is a projector
+        assert np.abs(G @ G - G).max() < 1e-8
+    else:
+        assert abs(np.linalg.norm(Wg) - 1) < 1e-10 and abs(np.linalg.norm(Mc) - 1) < 1e-10
+    if tag == "e32_b8_f8":
+        bits = oracle.hairy_bitstrings(10, 10, centre=5)
+        enc = [oracle.class_encode(oracle.encode_image(im, 32)[0], int(l), bits) for im, l in zip(x[:8], y[:8])]
+        S4 = _left_cut_singular_values(enc, 8)[3]      # bond 4: 16 -> 8
+        assert abs(S4[7] - S4[8]) < 1e-12 * S4[0]      # the cut is a tie: no unique answer
+        return
+    scale = np.abs(Wr).max()
+    if not ortho:
+        assert min(np.abs(Wg - Wr).max(), np.abs(Wg + Wr).max()) <= 1e-5 * scale
+    a, b = oracle.overlaps_dense(x, Wg), oracle.overlaps_dense(x, Wr)
+    assert np.abs(a - b).max() <= 1e-5 * b.max()
+    # and the classifier classifies: same predictions on the test images as the reference's
+    ov, _ = gpu_lib.classify(golden["x_test"], clf.data, D_encode, dtype="f64")
+    pred = golden[f"pred_{tag}_{'ortho' if ortho else 'nonortho'}"]
+    assert np.abs(ov - pred).max() <= 1e-5 * pred.max()
+
+
+def test_add_compress_groups_and_remainder(gpu_lib):
+    """adding_centre_batches semantics (experiments.py:497-509): consecutive groups, a shorter
+    remainder group at the end; each group equals the oracle's add + compress of its members —
+    without truncation (D = 32) and with a truncating D on D_encode = 10 images, whose summed site
+    matrices have no degenerate singular values at the cut."""
+    n = 23
+    y = np.arange(n) % 10
+    x = synthetic_images(n, seed=61, labels=y)
+    bits = oracle.hairy_bitstrings(10, 10, centre=5)
+    for D_enc, D in ((32, 32), (10, 8)):
+        mps = gpu_lib.mps_encoding(x, D_enc, dtype="f64")
+        mpos = gpu_lib.mpo_encoding(mps, y)
+        out = gpu_lib.adding_centre_batches(mpos, D, 5, orthogonalise=False)
+        assert len(out) == 5                                   # 5 + 5 + 5 + 5 + 3
+        enc = [oracle.class_encode(oracle.encode_image(im, D_enc, "sweep")[0], int(l), bits) for im, l in zip(x, y)]
+        ref = oracle.adding_centre_batches(enc, D, 5, False)
+        for g in range(5):
+            if D < D_enc:
+                for S in _left_cut_singular_values(enc[5 * g:5 * g + 5], D):
+                    assert len(S) <= D or S[D - 1] - S[D] > 1e-6 * S[0]   # clean cuts only
+            Wg = oracle.dense_classifier(out[g].data)
+            Wr = oracle.dense_classifier(oracle.real_sites(ref[g]))
+            assert min(np.abs(Wg - Wr).max(), np.abs(Wg + Wr).max()) <= 1e-8 * np.abs(Wr).max(), (D_enc, D, g)
+
+
+def test_mps_stacking_end_to_end(gpu_lib):
+    """experiments.py:528-643 with the stacking unitary BUILT on the device (class encoding, batch
+    adding at D_batch = 32, polar factor) from the fixture's training vectors: same accuracy as the
+    reference's run for n = 0..3 copies; for n <= 1 (no bond is truncated) the overlaps on the
+    training vectors — where the polar factor is unique — equal those of the reference's unitary."""
+    from orthogonal_classifiers_b200 import experiments as ex
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_stacking.npz"))
+    train = gpu_lib.mps_encoding(g["v_train"], None, dtype="f64")
+    test = gpu_lib.mps_encoding(g["v_test"], None, dtype="f64")
+    for n in range(4):
+        acc, preds, unitary = ex.mps_stacking(train, test, n, g["y_train"], g["y_test"], return_details=True)
+        L = 4 * (n + 1)
+        ref_unitary = [g[f"unitary_{n}_site_{i}"] for i in range(L)]
+        assert [w.shape for w in unitary.data] == [w.shape for w in ref_unitary]
+        assert acc == float(g[f"acc_{n}"])
+        if n <= 1:
+            mine = ex.stacked_predictions(train, unitary.data, n)
+            ref = ex.stacked_predictions(train, ref_unitary, n)
+            assert np.abs(mine - ref).max() <= 1e-8 * ref.max(), n
