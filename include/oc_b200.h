@@ -82,6 +82,10 @@ const char* oc_last_error(void);
  *   "ov_mma"   = 0  FFMA instead of tensor-core contractions in the overlap kernel
  *   "ov_pad"   = 0  D_encode < 32 images through the run-time-shaped overlap kernel
  *                   instead of zero-padded through the 32/32 one
+ *   "ov_tc5"   = 1  (default 0) natural 32/32 profile: site 4 as one shared-operand tcgen05.mma
+ *                   per CTA (images' A4^T E4 in tensor memory x classifier site in shared memory,
+ *                   3xTF32, accumulator in TMEM) instead of per-image mma.sync; measured 5.8 %
+ *                   slower than the default (profiles/tcgen05_r2.md), same overlaps
  *   "enc_events"    see oc_encode_step_ms
  *   "host_chunk" = n  images per pipeline stage of oc_classify_host (0 = default: 17,500 for
  *                   float pixels, 35,000 for uint8)

@@ -412,7 +412,7 @@ int overlap_impl(Ctx& cx, const void* mps_dev, const int32_t* mps_bonds_host, co
       key = fnv(key, &P.S, sizeof(P.S));
       key = fnv(key, P.a, sizeof(int) * (L + 1));
       key = fnv(key, P.B, sizeof(int) * (L + 1));
-      const int opts[3] = {oc::overlap_static_shapes(), oc::overlap_mma(), oc::overlap_pad()};
+      const int opts[4] = {oc::overlap_static_shapes(), oc::overlap_mma(), oc::overlap_pad(), oc::overlap_tc5()};
       key = fnv(key, opts, sizeof(opts));
       key |= 1ull;
       if (int rc = e.prepared.ensure(bytes, st)) return rc;
@@ -485,6 +485,10 @@ int oc_set_option(const char* key, int value) {
   }
   if (key && !strcmp(key, "ov_mma")) {
     oc::overlap_mma() = value;
+    return OC_OK;
+  }
+  if (key && !strcmp(key, "ov_tc5")) {
+    oc::overlap_tc5() = value;
     return OC_OK;
   }
   if (key && !strcmp(key, "ov_static")) {

@@ -37,7 +37,25 @@ struct OverlapFast {
   int a_total;                   // floats of the per-warp MPS staging
   int Spad;                      // label leg padded to a power of two >= 4
   int64_t wc_elems;              // floats of the re-laid hairy site: 2 * B_c * r4(B_{c+1}) * Spad
+  int w4u_off;                   // MODE 6: offset (floats) of site 4 as a tcgen05 B operand inside the small-W
+                                 // block (hi tile, then lo tile, 1024 floats each); -1: absent
 };
+
+// ---- MODE 6 (tcgen05): site 4 of the natural 32/32 profile as ONE shared-operand product per CTA ----
+// E5[(image, a')][B'] = sum_(s,B) Y[(image, a')][(s,B)] W4[(s,B)][B'],  Y = A4^T E4 per image (mma.sync):
+// the classifier site is the B operand of a tcgen05.mma (M = 128 = 4 images x 32 rows, N = 32, K = 32,
+// kind::tf32, 3xTF32), resident in shared memory in the no-swizzle K-major canonical layout
+// (core matrix = 8 rows x 16 bytes; LBO between 16-byte k chunks, SBO between 8-row groups);
+// the A operand (Y, hi / lo) and the accumulator live in tensor memory.
+constexpr int kTc5MaxA = 2752;                     // per-warp MPS staging of the natural plan (2,736 floats)
+constexpr int kTc5PerWarp = kTc5MaxA + 1024 + 2048 + 2 * 256 + 4;
+constexpr uint32_t kTc5Lbo = 128, kTc5Sbo = 1024;  // bytes
+constexpr int kTc5TileFloats = 1024;               // 32 x 32 fp32
+constexpr uint32_t kTc5Cols = 256;                 // TMEM columns: A hi/lo of tile t at 64 t / 64 t + 32, D at 128 + 32 t
+__host__ __device__ inline uint32_t tc5_kmaj_off(int row, int k) {  // byte offset of (row, k) in a K-major tile
+  return (uint32_t)(row >> 3) * kTc5Sbo + (uint32_t)(k >> 2) * kTc5Lbo + (uint32_t)(row & 7) * 16u + (uint32_t)(k & 3) * 4u;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo);
 
 // ---- classifier re-layout (one small launch per overlap call) --------------
 template <typename TIN>
@@ -72,6 +90,18 @@ __global__ void overlap_prep_kernel(const TIN* __restrict__ clf, OverlapParams P
         const int bp = i % Br, b = (i / Br) % Bl, s = i / (Br * Bl);
         small_w[F.w_off[n] + (int64_t)(s * Br + bp) * ld + b] = (float)W[i];
       }
+    }
+  }
+  if (F.w4u_off >= 0) {
+    // site 4 (2, 1, 16, 32) as the tcgen05 B operand [n = B'][k = (s,B)], split into TF32 hi / lo
+    const TIN* W = clf + P.clf_off[4];
+    for (int i = tid; i < 2 * 16 * 32; i += nth) {
+      const int bp = i & 31, k = i >> 5;  // k = s * 16 + B
+      uint32_t hi, lo;
+      split_tf32((float)W[i], hi, lo);
+      const int o = (int)(tc5_kmaj_off(bp, k) >> 2);
+      small_w[F.w4u_off + o] = __uint_as_float(hi);
+      small_w[F.w4u_off + kTc5TileFloats + o] = __uint_as_float(lo);
     }
   }
 }
@@ -356,6 +386,12 @@ __device__ __forceinline__ void mma_static(float* __restrict__ C, const float* _
         const int r = 16 * mt + g, col = 8 * nt + 2 * t;
         float* c0 = C + s * OFFC + r * LDC + swz<CSW>(r, col);
         float* c1 = C + s * OFFC + (r + 8) * LDC + swz<CSW>(r + 8, col);
+        if constexpr (CSW == 132) {
+          // rows of LDC = 32 floats holding the slices side by side (OFFC columns apart); the 16-byte chunks
+          // of row r rotated by r & 7 so that lane = row reads its row with conflict-free 128-bit loads
+          c0 = C + r * LDC + ((s * OFFC + col) ^ ((r & 7) << 2));
+          c1 = C + (r + 8) * LDC + ((s * OFFC + col) ^ (((r + 8) & 7) << 2));
+        }
         *reinterpret_cast<float2*>(c0) = make_float2(acc[s][mt][nt][0], acc[s][mt][nt][1]);
         *reinterpret_cast<float2*>(c1) = make_float2(acc[s][mt][nt][2], acc[s][mt][nt][3]);
       }
@@ -410,7 +446,8 @@ __device__ __forceinline__ void mm_static_pair(float* __restrict__ C0, const flo
 }
 
 // left step n (sites 0..3) and right step 9 - n side by side; R ping-pongs between Rcur and Rnext
-template <int NSITE, int CSW1 = 0, int CSW0 = 0>
+// SWAPL: the left problem's result transposed, E'[a'][B'] instead of Et'[B'][a'] (same shape when ar == Br)
+template <int NSITE, int CSW1 = 0, int CSW0 = 0, bool SWAPL = false>
 __device__ __forceinline__ void nat_pair_step(float* E, float* Tb, const float* W, const float* A, const float* Rcur,
                                               float* Rnext, const float* Wt, const float* At, int lane) {
   constexpr int al = 1 << NSITE, ar = 2 << NSITE, Bl = al, Br = ar;
@@ -419,8 +456,41 @@ __device__ __forceinline__ void nat_pair_step(float* E, float* Tb, const float* 
   mm_static_pair<al, Br, Bl, 2, ldT, al * ldT, ldE, 0, ldW, Bl * ldW>(Tb, E, W, Tb + 1024, Rcur, At, lane);
   __syncwarp();
   // Et'[B'][a'] = sum_(s,a) T[(s,a)][B'] A[(s,a)][a']   ||   R'[a][B] = sum_(s,B') T'[(s,B')][a] Wt[(s,B')][B]
-  mm_static_pair<Br, ar, 2 * al, 1, ldA, 0, ldT, 0, ldA, 0, CSW1, CSW0>(E, Tb, A, Rnext, Tb + 1024, Wt, lane);
+  if constexpr (SWAPL) {
+    static_assert(ar == Br && ldA == ldT, "transposed left result needs a square step");
+    mm_static_pair<Br, ar, 2 * al, 1, ldA, 0, ldT, 0, ldA, 0, CSW1, CSW0>(E, A, Tb, Rnext, Tb + 1024, Wt, lane);
+  } else {
+    mm_static_pair<Br, ar, 2 * al, 1, ldA, 0, ldT, 0, ldA, 0, CSW1, CSW0>(E, Tb, A, Rnext, Tb + 1024, Wt, lane);
+  }
   __syncwarp();
+}
+
+// ---- tcgen05 helpers (MODE 6) ----
+__device__ __forceinline__ uint64_t tc5_smem_desc(uint32_t saddr) {  // K-major, no swizzle, descriptor version 1
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((kTc5Lbo >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((kTc5Sbo >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor], kind::tf32, issued by one thread for the CTA
+__device__ __forceinline__ void tc5_mma(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc5_st16(uint32_t taddr, const uint32_t (&v)[16]) {  // lane = TMEM lane, 16 columns
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc5_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
 }
 
 template <int NSITE>
@@ -516,19 +586,34 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 1)
 overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_constant__ OverlapFast F,
                     const float* __restrict__ small_w, const float* __restrict__ wc) {
-  constexpr bool NAT = MODE >= 1 && MODE <= 3, MMA = MODE == 2 || MODE == 3, PAD = MODE == 3;
+  constexpr bool TC5 = MODE == 6;
+  constexpr bool NAT = (MODE >= 1 && MODE <= 3) || TC5, MMA = MODE == 2 || MODE == 3 || TC5, PAD = MODE == 3;
   constexpr bool LAST = MODE == 4 || MODE == 5, LMMA = MODE == 5;
   extern __shared__ __align__(128) unsigned char smem_ov[];
   float* sW = reinterpret_cast<float*>(smem_ov);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  constexpr int PER_WARP = kOvPerWarp;
+  constexpr int PER_WARP = TC5 ? kTc5PerWarp : kOvPerWarp;
+  constexpr int MAXA = TC5 ? kTc5MaxA : kOvMaxA;
   float* wbase = sW + ((F.small_w_total + 31) & ~31) + (size_t)warp * PER_WARP;
   float* As = wbase;
-  float* Eb = As + kOvMaxA;
+  float* Eb = As + MAXA;
   float* Tb = Eb + kOvE;
   float* Rb0 = Tb + kOvT;
   float* Rb1 = Rb0 + kOvR;
   __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(8) unsigned long long mbar_tc;  // TC5: completion of the CTA's tcgen05.mma batch
+  __shared__ uint32_t tmem_base_s;
+  if constexpr (TC5) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&mbar_tc)));
+    }
+    if (warp == 0) {  // one CTA per SM (213 KB of shared memory): the allocation cannot contend
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       (unsigned)__cvta_generic_to_shared(&tmem_base_s)), "n"(kTc5Cols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
 
   // ---- one bulk TMA copy of the small classifier sites into shared memory ----
   if (threadIdx.x == 0) {
@@ -560,6 +645,11 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
     }
   }
 
+  uint32_t tmem_base = 0;
+  if constexpr (TC5) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_base = tmem_base_s;  // written before the __syncthreads above
+  }
   const int c = P.c, L = P.L, S = P.S;
   // ---- per-CTA staging table: element e of an image block -> offset in As.
   //      left sites keep [s][a][a'] (ld r4(a')), hairy and right sites are
@@ -624,9 +714,10 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
     }
   };
   if constexpr (PAD || LAST) {
-    for (int i = lane; i < kOvMaxA; i += 32) As[i] = 0.f;  // the padding stays zero: the scatter never touches it
+    for (int i = lane; i < MAXA; i += 32) As[i] = 0.f;  // the padding stays zero: the scatter never touches it
     __syncwarp();
   }
+  [[maybe_unused]] unsigned tc_phase = 0u;  // TC5: parity of the CTA iteration's tcgen05 completion
   if (vec && (int64_t)blockIdx.x * nwarps + warp < P.N) prefetch((int64_t)blockIdx.x * nwarps + warp);
   // the trip count is per CTA (the tensor-core label sums below are CTA-wide); a warp whose image
   // index runs past N only takes part in the barriers
@@ -750,7 +841,70 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       if (lane == 0) { E[0] = 1.f; Rb0[0] = 1.f; }
       __syncwarp();
       const int64_t nxt_img = img + (int64_t)gridDim.x * nwarps;
-      if constexpr (MMA) {
+      if constexpr (TC5) {
+        // sites 0..3 and 9..6 side by side; the last left step leaves E4 a-major, E4[a'][B'] (rows of 16)
+        nat_pair_step<0>(E, Tb, sW + F.w_off[0], As + F.a_off[0], Rb0, Rb1, sW + F.w_off[9], As + F.a_off[9], lane);
+        nat_pair_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], Rb1, Rb0, sW + F.w_off[8], As + F.a_off[8], lane);
+        if (vec && nxt_img < P.N) prefetch_part(nxt_img, 1);
+        nat_pair_step<2>(E, Tb, sW + F.w_off[2], As + F.a_off[2], Rb0, Rb1, sW + F.w_off[7], As + F.a_off[7], lane);
+        nat_pair_step<3, 16, 16, true>(E, Tb, sW + F.w_off[3], As + F.a_off[3], Rb1, Rb0, sW + F.w_off[6],
+                                       As + F.a_off[6], lane);
+        if (vec && nxt_img < P.N) prefetch_part(nxt_img, 2);
+        // image first: Y[a'][(s,B)] = sum_a A4[(s,a)][a'] E4[a][B]  (mma.sync, per image) ...
+        mma_static<32, 16, 16, 2, 32, 16, 132, 32, 512, 16, 0>(Tb, As + F.a_off[4], E, lane);
+        __syncwarp();
+        // ... then the classifier site as the SHARED operand of one tcgen05 product per CTA:
+        // row a' = lane of Y, split into TF32 hi / lo, to tensor memory (A operand: lane = row, column = k)
+        {
+          const float* yr = Tb + lane * 32;
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 64u * (uint32_t)(warp >> 2);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = 4 * half + jj;
+              const float4 v = *reinterpret_cast<const float4*>(yr + ((j ^ (lane & 7)) << 2));
+              split_tf32(v.x, hi[4 * jj], lo[4 * jj]);
+              split_tf32(v.y, hi[4 * jj + 1], lo[4 * jj + 1]);
+              split_tf32(v.z, hi[4 * jj + 2], lo[4 * jj + 2]);
+              split_tf32(v.w, hi[4 * jj + 3], lo[4 * jj + 3]);
+            }
+            tc5_st16(ta + 16u * half, hi);
+            tc5_st16(ta + 32u + 16u * half, lo);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        {
+          // the valid warps of this CTA iteration (warp 0 always is one of them) meet; thread 0 issues
+          const int nvalid = (int)(P.N - base < (int64_t)nwarps ? P.N - base : (int64_t)nwarps);
+          asm volatile("bar.sync 1, %0;" ::"r"(32 * nvalid) : "memory");
+          if (threadIdx.x == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // D = f32, A = B = TF32, K-major, N = 32, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t bH = (uint32_t)__cvta_generic_to_shared(sW + F.w4u_off);
+            const uint32_t bL = bH + 4u * kTc5TileFloats;
+            const int tiles = nvalid > 4 ? 2 : 1;
+            for (int tl = 0; tl < tiles; ++tl) {
+              const uint32_t dcol = tmem_base + 128u + 32u * tl, ah = tmem_base + 64u * tl, al = ah + 32u;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t o = (uint32_t)ks * 2u * kTc5Lbo;  // 8 tf32 = two 16-byte chunks along K
+                tc5_mma(dcol, al + 8u * ks, tc5_smem_desc(bH + o), idesc, ks > 0);
+                tc5_mma(dcol, ah + 8u * ks, tc5_smem_desc(bL + o), idesc, 1u);
+                tc5_mma(dcol, ah + 8u * ks, tc5_smem_desc(bH + o), idesc, 1u);
+              }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(&mbar_tc))
+                         : "memory");
+          }
+          __syncwarp();
+        }
+      } else if constexpr (MMA) {
         // sites 0..3 and 9..6 side by side (one half-warp each), then site 4
         nat_pair_step<0>(E, Tb, sW + F.w_off[0], As + F.a_off[0], Rb0, Rb1, sW + F.w_off[9], As + F.a_off[9], lane);
         nat_pair_step<1>(E, Tb, sW + F.w_off[1], As + F.a_off[1], Rb1, Rb0, sW + F.w_off[8], As + F.a_off[8], lane);
@@ -784,8 +938,40 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       float* G = Tb;                      // [s][a][B']
       float* H = Tb + 1024;               // [s][B][B']
       if constexpr (MMA) {
-        mma_static<32, 16, 16, 2, 16, 512, 16, 16, 512, 16, 0, true>(G, At, R, lane);
+        mma_static<32, 16, 16, 2, 16, 512, 16, 16, 512, 16, 0, true>(G, At, R, lane);  // independent of E5
         __syncwarp();
+        if constexpr (TC5) {
+          // E5[a'][B'] of this image out of tensor memory: lane = a', rows of 32 floats, swz<32>
+          const unsigned bar = (unsigned)__cvta_generic_to_shared(&mbar_tc);
+          unsigned done = 0;
+          for (int spin = 0; !done; ++spin) {
+            if (spin > (1 << 24)) __trap();  // a lost completion must not hang the GPU
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar), "r"(tc_phase)
+                : "memory");
+          }
+          tc_phase ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t td = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 128u + 32u * (uint32_t)(warp >> 2);
+          float* er = E + lane * 32;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t d[16];
+            tc5_ld16(td + 16u * half, d);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = 4 * half + jj;
+              *reinterpret_cast<float4*>(er + ((j ^ ((lane & 3) << 1)) << 2)) =
+                  make_float4(__uint_as_float(d[4 * jj]), __uint_as_float(d[4 * jj + 1]), __uint_as_float(d[4 * jj + 2]),
+                              __uint_as_float(d[4 * jj + 3]));
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+        }
         mma_static<32, 16, 32, 2, 16, 512, 0, 32, 0, 16, 512>(H, E, G, lane);
       } else {
         mm_static<32, 16, 16, 2, 16, 32 * 16, 32, 16 * 32, 16, 0>(G, At, R, lane);
@@ -954,7 +1140,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       __syncthreads();  // every warp's H is in its scratch
       {
         const int g = lane >> 2, t = lane & 3;
-        const float* hb = sW + ((F.small_w_total + 31) & ~31) + (size_t)g * PER_WARP + kOvMaxA + kOvE + 1024 +
+        const float* hb = sW + ((F.small_w_total + 31) & ~31) + (size_t)g * PER_WARP + MAXA + kOvE + 1024 +
                           128 * warp;            // H of image g (warp g), this warp's rows
         const float* wcw = wc + (size_t)(128 * warp) * 16;
         float acc4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -982,7 +1168,7 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
         // warp = image: lane l < 16 adds the 8 partial sums of label l
         float v = 0.f;
         if (lane < 16) {
-          const float* rb = sW + ((F.small_w_total + 31) & ~31) + kOvMaxA + kOvE + lane * 8 + warp;
+          const float* rb = sW + ((F.small_w_total + 31) & ~31) + MAXA + kOvE + lane * 8 + warp;
 #pragma unroll
           for (int w2 = 0; w2 < 8; ++w2) v += rb[(size_t)w2 * PER_WARP];
         }
@@ -1003,6 +1189,11 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       __syncthreads();  // the partial sums are read before anyone's next G overwrites them
     }
   }
+  if constexpr (TC5) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTc5Cols));
+  }
 }
 
 inline int& overlap_static_shapes() {
@@ -1017,9 +1208,14 @@ inline int& overlap_pad() {
   static int v = 1;
   return v;
 }
+// MODE 6: site 4 of the natural 32/32 profile on tcgen05 (measured against MODE 2 in profiles/; off by default)
+inline int& overlap_tc5() {
+  static int v = 0;
+  return v;
+}
 
 // Host-side plan; returns false when the shapes do not fit the fast kernel.
-inline bool overlap_fast_plan(const OverlapParams& P, OverlapFast& F) {
+inline bool overlap_fast_plan(const OverlapParams& P, OverlapFast& F, bool allow_tc5 = true) {
   if (P.L > OC_MAX_SITES || P.amax > 32 || P.Bmax > 32 || P.S > 32) return false;
   int64_t w = 0, a = 0;
   for (int n = 0; n < P.L; ++n) {
@@ -1039,6 +1235,12 @@ inline bool overlap_fast_plan(const OverlapParams& P, OverlapFast& F) {
       if (n < P.c && (2 * al * r4(Br) > kOvT || Br * r4(ar) > kOvE || ar * r4(Br) > kOvE)) return false;
       if (n > P.c && (2 * Br * r4(al) > kOvT || al * r4(Bl) > kOvR || ar * r4(Br) > kOvR)) return false;
     }
+  }
+  F.w4u_off = -1;
+  if (allow_tc5 && overlap_tc5() && overlap_static_shapes() && overlap_mma() && overlap_is_natural(P) && P.S == 16) {
+    w = (w + 31) & ~31LL;  // 128-byte aligned operand tiles
+    F.w4u_off = (int)w;
+    w += 2 * kTc5TileFloats;
   }
   if (w > kOvMaxSmallW || a > kOvMaxA || a > 65535 || P.mps_stride > 16384) return false;
   F.small_w_total = (int)w;
@@ -1071,7 +1273,7 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   float* small_w = scratch_dev;
   float* wc = scratch_dev + ((F.small_w_total + 31) & ~31);
   int warps = 8;
-  constexpr int PER_WARP = kOvPerWarp;
+  const int PER_WARP = F.w4u_off >= 0 ? kTc5PerWarp : kOvPerWarp;
   const size_t wbytes = (size_t)((F.small_w_total + 31) & ~31) * 4;
   const size_t tabbytes = (((size_t)P.mps_stride * 2 + 15) & ~(size_t)15) + 16;
   while (warps > 1 && wbytes + tabbytes + (size_t)warps * PER_WARP * 4 > 222 * 1024) --warps;
@@ -1085,7 +1287,7 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
     OverlapParams Pn = P;
     for (int n = 0; n <= 10; ++n) Pn.a[n] = n <= 5 ? (1 << n) : (1 << (10 - n));
     Pn.amax = 32;
-    if (!overlap_fast_plan(Pn, F)) return -1;
+    if (!overlap_fast_plan(Pn, F, false)) return -1;  // same small-W block as the first plan (no tcgen05 tile)
   }
   const bool mma = (nat || pad) && overlap_mma() && warps == 8;
   const bool lmma = last && overlap_mma();
@@ -1110,6 +1312,8 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(overlap_fast_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(overlap_fast_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t need = (P.N + warps - 1) / warps;
@@ -1120,6 +1324,8 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
     overlap_fast_kernel<4><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   else if (mma && pad)
     overlap_fast_kernel<3><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
+  else if (mma && F.w4u_off >= 0 && warps == 8)
+    overlap_fast_kernel<6><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   else if (mma)
     overlap_fast_kernel<2><<<grid, warps * 32, smem, st>>>(P, F, small_w, wc);
   else if (nat)

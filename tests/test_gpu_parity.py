@@ -345,6 +345,30 @@ def test_alternative_code_paths_agree(gpu_lib, option):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n_img", [1, 5, 8 * 148 + 3, 4099])
+def test_tcgen05_overlap_mode_matches_mma_sync(gpu_lib, n_img):
+    """``ov_tc5`` (opt-in, MODE 6 of the overlap kernel): site 4 of the natural 32/32 profile as one
+    shared-operand tcgen05.mma per CTA (A = the images' Y = A4^T E4 in tensor memory, B = the classifier
+    site in shared memory, 3xTF32, accumulator in TMEM).  Same overlaps as the mma.sync kernel (MODE 2)
+    and as the dense fp64 oracle, for full CTA iterations, a ragged last one and fewer images than a tile."""
+    from orthogonal_classifiers_b200 import batched
+    imgs = synthetic_images(n_img, seed=31).astype(np.float32)
+    clf = random_classifier(10, 32, centre=5, seed=6)
+    enc = gpu_lib.encode_images(imgs, 32)
+    ov_mma = gpu_lib.label_overlaps(enc, clf)
+    batched.set_option("ov_tc5", 1)
+    try:
+        ov_tc5 = gpu_lib.label_overlaps(enc, clf)
+        ov_tc5_again = gpu_lib.label_overlaps(enc, clf)   # a second launch: fresh TMEM allocation, same bits
+    finally:
+        batched.set_option("ov_tc5", 0)
+    ref = oracle.overlaps_dense(imgs, oracle.dense_classifier(clf))
+    assert np.abs(ov_tc5 - ov_mma).max() <= 1e-5 * ref.max()
+    assert np.abs(ov_tc5 - ref).max() <= 1e-5 * ref.max()
+    assert np.array_equal(ov_tc5, ov_tc5_again)
+
+
+@pytest.mark.gpu
 def test_two_stream_chunk_split_is_bit_identical(gpu_lib):
     """``enc_split2`` (opt-in): the two halves of an encoder chunk run on two
     streams and rejoin the caller's stream.  An image's MPS does not depend on
