@@ -683,10 +683,13 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       else d = (sdx * AR + ap) * r4(AL) + a;
     } else if (n < c) {
       d = q * r4(ar) + ap;
+      if (MMA && n == 4) d = q * 32 + swz<32>(q, ap);  // fragment operand of the site-4 contraction
     } else {
       const int sdx = q / al, a = q - sdx * al;
       d = (sdx * ar + ap) * r4(al) + a;
-      if (MMA && n == c) d = (sdx * ar + ap) * 32 + swz<32>(ap, a);  // fragment operand of G
+      // natural profile, tensor-core path: site 5 keeps its [s][a][a'] layout (the m-major operand of G),
+      // its 16-byte quads swizzled
+      if (MMA && n == c) d = sdx * 512 + a * 16 + ((((ap >> 2) ^ ((a >> 1) & 3)) << 2) | (ap & 3));
     }
     tab[e] = (unsigned short)(F.a_off[n] + d);
   }
@@ -731,7 +734,9 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
       for (int j = 0; j < kOvPre; ++j) {
         const int v = lane + 32 * j;
         if (MMA && !PAD && v >= 341 && v <= 596) {
-          // site 5 keeps its [s][a][a'] layout (the m-major operand of G), quads swizzled
+          // site 5 keeps its [s][a][a'] layout (the m-major operand of G), quads swizzled.  (The places
+          // are computed, not read from the staging table: a table load in front of every store measured
+          // 525 vs 519 us - the kernel is bound by latency, not by its instruction count.)
           const int i = 4 * v - 1364;
           const int a = (i >> 4) & 31, q = (i >> 2) & 3;
           *reinterpret_cast<float4*>(As + 1368 + (i & ~15) + ((q ^ ((a >> 1) & 3)) << 2)) = pre[j];
