@@ -86,6 +86,9 @@ const char* oc_last_error(void);
  *                   per CTA (images' A4^T E4 in tensor memory x classifier site in shared memory,
  *                   3xTF32, accumulator in TMEM) instead of per-image mma.sync; measured 5.8 %
  *                   slower than the default (profiles/tcgen05_r2.md), same overlaps
+ *   "fused_sweep" = 0  oc_encode_classify / oc_classify_host with OC_TRUNC_SWEEP: bring the MPS back to
+ *                   the left-canonical gauge before the overlap (as oc_encode_batch does) instead of
+ *                   contracting the right-canonical MPS the right-to-left sweep leaves (same overlaps)
  *   "enc_events"    see oc_encode_step_ms
  *   "host_chunk" = n  images per pipeline stage of oc_classify_host (0 = default: 17,500 for
  *                   float pixels, 35,000 for uint8)

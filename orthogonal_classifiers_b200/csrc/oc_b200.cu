@@ -129,6 +129,7 @@ struct Ctx {
 std::mutex g_ctx_mu;
 std::map<std::pair<int, void*>, std::unique_ptr<Ctx>> g_ctx;
 int g_force_generic = 0;
+int g_fused_sweep = 1;  // oc_encode_classify / oc_classify_host, OC_TRUNC_SWEEP: overlaps from the right-canonical MPS
 int g_host_chunk = 0;  // 0 = default per input type
 int g_host_ramp = 1;
 
@@ -343,6 +344,59 @@ int encode_impl(Ctx& cx, const void* images_dev, int in_dtype, int64_t N, int n_
                        sweeps_out_dev, st);
 }
 
+// The first two stages of OC_TRUNC_SWEEP only (fp32): bit reversal | inline chain.  mps_out receives, per image,
+// the chain of the bit-reversed image = the right-canonical MPS of the truncated state with positions and
+// bond indices mirrored (OverlapParams::mirrored); the gauge pass of encode_sweep_t is left out.
+int encode_mirrored_f32(Ctx& cx, const void* images_dev, int in_dtype, int64_t N, int n_pix, int64_t ld, int L, int D,
+                        void* mps_out_dev, int64_t mps_stride, cudaStream_t st) {
+  const int cap = 1 << L;
+  const size_t in_esz = in_dtype == OC_F32 ? 4 : (in_dtype == OC_F64 ? 8 : 1);
+  const int64_t chunk = std::min<int64_t>(N, kSweepChunk);
+  if (int rc = cx.sw_img.ensure((size_t)chunk * cap * sizeof(float), st)) return rc;
+  for (int64_t lo = 0; lo < N; lo += kSweepChunk) {
+    const int64_t n = std::min<int64_t>(kSweepChunk, N - lo);
+    const char* src = reinterpret_cast<const char*>(images_dev) + (size_t)lo * ld * in_esz;
+    float* rimg = reinterpret_cast<float*>(cx.sw_img.p);
+    oc::sweep::bitrev_kernel<float><<<(int)std::min<int64_t>(n, (int64_t)num_sms() * 8), 256, 0, st>>>(
+        src, in_dtype, n, n_pix, ld, L, rimg);
+    OC_CUDA(cudaGetLastError());
+    if (int rc = encode_inline(cx, rimg, OC_F32, n, cap, cap, L, D, OC_F32,
+                               reinterpret_cast<float*>(mps_out_dev) + (size_t)lo * mps_stride, nullptr, nullptr, st))
+      return rc;
+  }
+  return OC_OK;
+}
+
+int overlap_impl(Ctx& cx, const void* mps_dev, const int32_t* mps_bonds_host, const void* clf_dev,
+                 const int32_t* clf_bonds_host, const int32_t* clf_s_host, int L, int64_t N, int dtype,
+                 void* overlaps_out_dev, int32_t* argmax_out_dev, cudaStream_t st, int signed_out, int mirrored,
+                 bool* fast_ok);
+
+// encode + classify of device-resident images through the workspace `ws` (N MPS blocks).  With
+// OC_TRUNC_SWEEP and a D that truncates, the overlaps are taken from the right-canonical MPS the
+// right-to-left sweep leaves (same state, another gauge): no pass back to the left gauge.
+int encode_classify_impl(Ctx& cx, const void* images_dev, int in_dtype, int64_t N, int n_pix, int64_t ld, int L, int D,
+                         int dtype, int trunc_mode, const void* clf_dev, const int32_t* clf_bonds_host,
+                         const int32_t* clf_s_host, const int32_t* bonds, int64_t mps_stride, void* ws,
+                         void* overlaps_out_dev, int32_t* argmax_out_dev, cudaStream_t st) {
+  const bool truncates = clampD(L, D) < (1 << (L / 2));
+  if (trunc_mode == OC_TRUNC_SWEEP && truncates && dtype == OC_F32 && g_fused_sweep) {
+    bool ok = false;
+    if (int rc = overlap_impl(cx, nullptr, bonds, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype, nullptr, nullptr, st,
+                              0, 1, &ok))
+      return rc;
+    if (ok) {
+      if (int rc = encode_mirrored_f32(cx, images_dev, in_dtype, N, n_pix, ld, L, D, ws, mps_stride, st)) return rc;
+      return overlap_impl(cx, ws, bonds, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype, overlaps_out_dev,
+                          argmax_out_dev, st, 0, 1, nullptr);
+    }
+  }
+  if (int rc = encode_impl(cx, images_dev, in_dtype, N, n_pix, ld, L, D, dtype, trunc_mode, ws, nullptr, nullptr, st))
+    return rc;
+  return overlap_impl(cx, ws, bonds, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype, overlaps_out_dev,
+                      argmax_out_dev, st, 0, 0, nullptr);
+}
+
 uint64_t fnv(uint64_t h, const void* p, size_t n) {
   const unsigned char* b = reinterpret_cast<const unsigned char*>(p);
   for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
@@ -351,13 +405,19 @@ uint64_t fnv(uint64_t h, const void* p, size_t n) {
 
 int overlap_impl(Ctx& cx, const void* mps_dev, const int32_t* mps_bonds_host, const void* clf_dev,
                  const int32_t* clf_bonds_host, const int32_t* clf_s_host, int L, int64_t N, int dtype,
-                 void* overlaps_out_dev, int32_t* argmax_out_dev, cudaStream_t st, int signed_out = 0) {
+                 void* overlaps_out_dev, int32_t* argmax_out_dev, cudaStream_t st, int signed_out = 0,
+                 int mirrored = 0, bool* fast_ok = nullptr);
+int overlap_impl(Ctx& cx, const void* mps_dev, const int32_t* mps_bonds_host, const void* clf_dev,
+                 const int32_t* clf_bonds_host, const int32_t* clf_s_host, int L, int64_t N, int dtype,
+                 void* overlaps_out_dev, int32_t* argmax_out_dev, cudaStream_t st, int signed_out, int mirrored,
+                 bool* fast_ok) {
+  // fast_ok != nullptr: dry run - only report whether the specialised kernel takes these shapes
   if (N < 0) return fail(OC_E_ARG, "N=%lld < 0", (long long)N);
   if (L < 1 || L > OC_MAX_SITES) return fail(OC_E_ARG, "L=%d outside [1,%d]", L, OC_MAX_SITES);
   if (dtype != OC_F32 && dtype != OC_F64) return fail(OC_E_ARG, "bad dtype %d", dtype);
-  if (N == 0) return OC_OK;
-  if (!mps_dev || !clf_dev || !overlaps_out_dev || !mps_bonds_host || !clf_bonds_host || !clf_s_host)
-    return fail(OC_E_ARG, "null pointer argument");
+  if (N == 0 && !fast_ok) return OC_OK;
+  if (!fast_ok && (!mps_dev || !clf_dev || !overlaps_out_dev)) return fail(OC_E_ARG, "null pointer argument");
+  if (!mps_bonds_host || !clf_bonds_host || !clf_s_host) return fail(OC_E_ARG, "null pointer argument");
 
   oc::OverlapParams P;
   memset(&P, 0, sizeof(P));
@@ -397,6 +457,12 @@ int overlap_impl(Ctx& cx, const void* mps_dev, const int32_t* mps_bonds_host, co
   P.overlaps = overlaps_out_dev;
   P.argmax = argmax_out_dev;
   P.signed_out = signed_out;
+  P.mirrored = mirrored;
+  if (fast_ok) {
+    *fast_ok = dtype == OC_F32 && !g_force_generic && oc::overlap_fast_supported(P) && !oc::overlap_is_natural(P);
+    for (int n = 0; n <= L; ++n) *fast_ok = *fast_ok && P.a[n] == P.a[L - n];
+    return OC_OK;
+  }
 
   if (dtype == OC_F32 && !g_force_generic && oc::overlap_fast_supported(P)) {
     const size_t bytes = oc::overlap_fast_scratch_floats(P) * sizeof(float);
@@ -429,6 +495,7 @@ int overlap_impl(Ctx& cx, const void* mps_dev, const int32_t* mps_bonds_host, co
     if (rc == 0) return OC_OK;
     if (rc > 0) return fail(OC_E_CUDA, "overlap_fast launch failed: %s", cudaGetErrorString((cudaError_t)rc));
   }
+  if (mirrored) return fail(OC_E_ARG, "internal: mirrored MPS outside the specialised overlap kernel");
 
   const size_t esz = dtype == OC_F32 ? 4 : 8;
   const size_t per_warp = ((size_t)5 * P.amax * P.Bmax + 64) * esz;
@@ -485,6 +552,14 @@ int oc_set_option(const char* key, int value) {
   }
   if (key && !strcmp(key, "ov_mma")) {
     oc::overlap_mma() = value;
+    return OC_OK;
+  }
+  if (key && !strcmp(key, "fused_sweep")) {
+    g_fused_sweep = value;
+    return OC_OK;
+  }
+  if (key && !strcmp(key, "ov_warps")) {
+    oc::overlap_max_warps() = value;
     return OC_OK;
   }
   if (key && !strcmp(key, "ov_tc5")) {
@@ -632,10 +707,8 @@ int oc_encode_classify(const void* images_dev, int in_dtype, int64_t N, int n_pi
     if (int rc = cx.mps.ensure((size_t)N * offs[L] * esz, st)) return rc;
     ws = cx.mps.p;
   }
-  if (int rc = encode_impl(cx, images_dev, in_dtype, N, n_pix, ld, L, D, dtype, trunc_mode, ws, nullptr, nullptr, st))
-    return rc;
-  return overlap_impl(cx, ws, bonds, clf_dev, clf_bonds_host, clf_s_host, L, N, dtype, overlaps_out_dev,
-                      argmax_out_dev, st);
+  return encode_classify_impl(cx, images_dev, in_dtype, N, n_pix, ld, L, D, dtype, trunc_mode, clf_dev, clf_bonds_host,
+                              clf_s_host, bonds, offs[L], ws, overlaps_out_dev, argmax_out_dev, st);
 }
 
 int oc_class_encode(const void* mps_dev, int mps_dtype, int64_t N, int L, const int32_t* mps_bonds_host,
@@ -900,14 +973,12 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
                             cudaMemcpyHostToDevice, hp.copy));
     OC_CUDA(cudaEventRecord(hp.copied[b], hp.copy));
     OC_CUDA(cudaStreamWaitEvent(st, hp.copied[b], 0));
-    if (int rc = encode_impl(cx, hp.stage[b].p, in_dtype, n, n_pix, ld, L, D, dtype, trunc_mode, hp.mps.p, nullptr,
-                             nullptr, st))
+    if (k >= 2) OC_CUDA(cudaStreamWaitEvent(st, hp.backdone[b], 0));  // results of chunk k - 2 have left ov[b] / am[b]
+    if (int rc = encode_classify_impl(cx, hp.stage[b].p, in_dtype, n, n_pix, ld, L, D, dtype, trunc_mode, hp.clf.p,
+                                      clf_bonds_host, clf_s_host, bonds, offs[L], hp.mps.p, hp.ov[b].p,
+                                      reinterpret_cast<int32_t*>(hp.am[b].p), st))
       return rc;
     OC_CUDA(cudaEventRecord(hp.freed[b], st));
-    if (k >= 2) OC_CUDA(cudaStreamWaitEvent(st, hp.backdone[b], 0));  // results of chunk k - 2 have left ov[b] / am[b]
-    if (int rc = overlap_impl(cx, hp.mps.p, bonds, hp.clf.p, clf_bonds_host, clf_s_host, L, n, dtype, hp.ov[b].p,
-                              reinterpret_cast<int32_t*>(hp.am[b].p), st))
-      return rc;
     OC_CUDA(cudaEventRecord(hp.done[b], st));
     OC_CUDA(cudaStreamWaitEvent(hp.back, hp.done[b], 0));
     OC_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(overlaps_out_host) + (size_t)lo * S * esz, hp.ov[b].p,

@@ -239,6 +239,11 @@ struct OverlapParams {
   void* overlaps;
   int32_t* argmax;  // nullable
   int signed_out;   // 1: store the signed label vector instead of its absolute values (argmax still on |.|)
+  // 1 (fast overlap kernel only): `mps` holds the chain of the BIT-REVERSED image, i.e. block position p is
+  // (2, a_{L-p}, a_{L-1-p}) with element (s, r, l) = site L-1-p's (s, l, r) - the right-canonical MPS the
+  // OC_TRUNC_SWEEP encoder has before its pass back to the left gauge (oc_sweep.cuh).  The overlaps do not
+  // depend on the gauge, so the fused encode + classify entry points skip that pass.  Needs a[n] == a[L-n].
+  int mirrored;
 };
 
 template <typename T>

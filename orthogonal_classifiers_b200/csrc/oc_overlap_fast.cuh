@@ -661,8 +661,20 @@ overlap_fast_kernel(const __grid_constant__ OverlapParams P, const __grid_consta
     int n = 0;
     while (n + 1 < L && e >= (int)P.mps_off[n + 1]) ++n;
     const int i = e - (int)P.mps_off[n];
+    int q, ap;  // element (s, a, a') of site n: q = s*al + a, ap = a'
+    if (P.mirrored) {
+      // block position n holds site L-1-n with its two bond indices swapped (symmetric bond profile:
+      // the positions' offsets are the sites' offsets)
+      n = L - 1 - n;
+      const int al_ = P.a[n], ar_ = P.a[n + 1];
+      const int y = i % al_, sx = i / al_;
+      q = (sx / ar_) * al_ + y;
+      ap = sx % ar_;
+    } else {
+      q = i / P.a[n + 1];
+      ap = i - q * P.a[n + 1];
+    }
     const int al = P.a[n], ar = P.a[n + 1];
-    const int q = i / ar, ap = i - q * ar;  // q = s*al + a
     int d;
     if constexpr (LAST) {
       // natural-profile destination; every site but the last keeps [s][a][a'] (ld r4(a')), the
@@ -1213,6 +1225,11 @@ inline int& overlap_pad() {
   static int v = 1;
   return v;
 }
+// diagnostics: upper bound on the warps per CTA (how does the kernel scale with resident warps?)
+inline int& overlap_max_warps() {
+  static int v = 8;
+  return v;
+}
 // MODE 6: site 4 of the natural 32/32 profile on tcgen05 (measured against MODE 2 in profiles/; off by default)
 inline int& overlap_tc5() {
   static int v = 0;
@@ -1277,12 +1294,13 @@ inline int overlap_fast_launch(const OverlapParams& P, float* scratch_dev, int s
   if (!overlap_fast_plan(P, F)) return -1;
   float* small_w = scratch_dev;
   float* wc = scratch_dev + ((F.small_w_total + 31) & ~31);
-  int warps = 8;
+  int warps = overlap_max_warps() < 8 && overlap_max_warps() > 0 ? overlap_max_warps() : 8;
   const int PER_WARP = F.w4u_off >= 0 ? kTc5PerWarp : kOvPerWarp;
   const size_t wbytes = (size_t)((F.small_w_total + 31) & ~31) * 4;
   const size_t tabbytes = (((size_t)P.mps_stride * 2 + 15) & ~(size_t)15) + 16;
   while (warps > 1 && wbytes + tabbytes + (size_t)warps * PER_WARP * 4 > 222 * 1024) --warps;
   const bool nat = overlap_static_shapes() && overlap_is_natural(P) && F.Spad == 16;
+  if (P.mirrored && overlap_is_natural(P)) return -1;  // (never asked for: an untruncated encoding has no sweep)
   // D_encode < 32 against the natural-32 classifier: the image sites are staged zero-padded to the
   // natural profile, so the shared-memory offsets are those of the natural plan
   const bool pad = overlap_static_shapes() && overlap_mma() && overlap_pad() && warps == 8 && F.Spad == 16 &&

@@ -369,6 +369,36 @@ def test_tcgen05_overlap_mode_matches_mma_sync(gpu_lib, n_img):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("D", [2, 4, 8, 10, 16, 20])
+def test_fused_sweep_classify_is_gauge_free(gpu_lib, D):
+    """encode + classify with the reference's truncation order (OC_TRUNC_SWEEP): the fused entry points contract
+    the RIGHT-canonical MPS the right-to-left truncating sweep leaves (block positions and bond indices mirrored,
+    `OverlapParams::mirrored`) instead of first sweeping back to the left gauge as `oc_encode_batch` must.
+    Same state, so the same overlaps - against the two-step path, for every kernel family (zero-padded natural-32
+    classifier, last-site-hairy, run-time shapes) and through the host-buffer call."""
+    from orthogonal_classifiers_b200 import batched
+    imgs = np.concatenate([synthetic_images(700, seed=41), adversarial_images()]).astype(np.float32)
+    for clf in (random_classifier(10, 32, centre=5, seed=7), random_classifier(10, 32, centre=9, seed=8),
+                random_classifier(10, 20, centre=5, seed=9), random_classifier(10, 12, centre=3, seed=10)):
+        ov_fused, am_fused = gpu_lib.classify(imgs, clf, D, trunc="sweep")
+        enc = gpu_lib.encode_images(imgs, D, trunc="sweep")            # left-canonical MPS, then the overlap
+        ov_two = gpu_lib.label_overlaps(enc, clf)
+        batched.set_option("fused_sweep", 0)
+        try:
+            ov_off, am_off = gpu_lib.classify(imgs, clf, D, trunc="sweep")
+        finally:
+            batched.set_option("fused_sweep", 1)
+        scale = ov_two.max()
+        assert np.abs(ov_fused - ov_two).max() <= 1e-5 * scale
+        assert np.abs(ov_off - ov_two).max() <= 1e-5 * scale
+        srt = np.sort(ov_two, axis=1)
+        tie = (srt[:, -1] - srt[:, -2]) < 1e-5 * scale
+        assert np.all((am_fused == ov_two.argmax(1)) | tie)
+        ov_host, am_host = gpu_lib.classify_host(imgs, clf, D, trunc="sweep")
+        assert np.abs(ov_host - ov_two).max() <= 1e-5 * scale
+
+
+@pytest.mark.gpu
 def test_two_stream_chunk_split_is_bit_identical(gpu_lib):
     """``enc_split2`` (opt-in): the two halves of an encoder chunk run on two
     streams and rejoin the caller's stream.  An image's MPS does not depend on
