@@ -988,7 +988,19 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
   const int64_t dflt = two ? (in_dtype == OC_U8 ? 17500 : 8750) : (in_dtype == OC_U8 ? 35000 : 17500);
   const int64_t base = std::min<int64_t>(g_host_chunk > 0 ? g_host_chunk : dflt, N);
   std::vector<int64_t> sizes;
-  {
+  if (const char* plan = getenv("OC_HOST_SIZES")) {  // diagnostics: explicit chunk sizes, e.g. "17500,17500,35000"
+    int64_t left = N;
+    for (const char* q = plan; *q && left > 0;) {
+      char* end = nullptr;
+      const long long v = strtoll(q, &end, 10);
+      if (end == q) break;
+      const int64_t c = std::min<int64_t>(std::max<long long>(v, 1), left);
+      sizes.push_back(c);
+      left -= c;
+      q = *end ? end + 1 : end;
+    }
+    if (left > 0) sizes.push_back(left);
+  } else {
     int64_t left = N;
     if (in_dtype == OC_U8 && g_host_ramp && !two && base >= 4096) {
       for (int64_t c : {base / 4, base / 2}) {
