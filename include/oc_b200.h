@@ -71,6 +71,8 @@ const char* oc_last_error(void);
  *   "enc_gram" = 0  steps 0-3 by Jacobi on the image unfoldings instead of the
  *                   16 x 16 Gram matrix
  *   "enc_pack" = 0  step 4 with 16 lanes per image instead of packed warps
+ *   "enc_mix"  = 0  packed step 4: only images with equally long lines share a warp (default 1: the
+ *                   idle lanes of a warp also take one image with a shorter line; bit-identical results)
  *   "enc_mgs4" = 0  step 4 without the Gram-Schmidt preconditioning
  *   "enc_qr5"  = 0  step 5 without the pivoted Gram-Schmidt preconditioning
  *   "enc_split5" = 0  step 5 as one kernel instead of three

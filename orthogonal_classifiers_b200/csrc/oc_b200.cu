@@ -618,6 +618,10 @@ int oc_set_option(const char* key, int value) {
     oc::hw::pack_step4() = value;
     return OC_OK;
   }
+  if (key && !strcmp(key, "enc_mix")) {
+    oc::hw::mix_step4() = value;
+    return OC_OK;
+  }
   if (key && !strcmp(key, "enc_gram")) {
     oc::gram::enabled() = value;
     return OC_OK;

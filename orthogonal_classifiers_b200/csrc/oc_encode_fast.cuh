@@ -504,12 +504,12 @@ __device__ __forceinline__ float* run_steps(const EncodeParams& P, int64_t img, 
 constexpr int kWsStride = 1024;
 // scratch behind the two Psi buffers for the pairing sort of the half-warp chain:
 // keys (1 byte / image) | perm (int32: 4 image slots per warp of the packed step 4, <= chunk/2 + 32 warps)
-// | 4 x 32 ints of bins
+// | 12 x 32 ints of bins (counts, starts, cursors, totals; own counts and guest records of the packed step 4)
 constexpr int kSortBins = 32;
 inline size_t encode_perm_ints(int64_t chunk) { return (size_t)(2 * chunk + 4 * kSortBins + 4); }
 inline size_t encode_sort_bytes(int64_t chunk) {
   return (size_t)((chunk + 255) & ~(int64_t)255) + encode_perm_ints(chunk) * sizeof(int32_t) +
-         (size_t)4 * kSortBins * sizeof(int32_t) + 256;
+         (size_t)12 * kSortBins * sizeof(int32_t) + 256;
 }
 
 template <int DPAD, int N0, int N1>

@@ -1006,17 +1006,22 @@ hw_row4q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t w = (int64_t)blockIdx.x * kHwWarps + warp;
   if (w >= bins[3 * kSortBins]) return;  // per-warp shared memory only: no block barrier below
+  // lane groups of the warp's (up to four) images: k_j lanes each, in list order; the first image has
+  // the longest line (hosts before guests, see hw_pack_prefix_kernel), empty list slots take no lanes
   const int4 ent = __ldg(reinterpret_cast<const int4*>(perm4) + w);
-  const int k0 = ent.x >= 0 ? (int)keys[ent.x] : 0;
-  const int gs = k0 > 1 ? k0 : 1;
-  const int ipw = 32 / gs < 4 ? 32 / gs : 4;
-  const int idx = lane / gs;
+  const int k0 = ent.x >= 0 ? max((int)keys[ent.x], 1) : 0;
+  const int k1 = ent.y >= 0 ? max((int)keys[ent.y], 1) : 0;
+  const int k2 = ent.z >= 0 ? max((int)keys[ent.z], 1) : 0;
+  const int k3 = ent.w >= 0 ? max((int)keys[ent.w], 1) : 0;
+  const int gs = max(max(max(k0, k1), max(k2, k3)), 1);  // longest line of the warp
+  const int b1 = k0, b2 = b1 + k1, b3 = b2 + k2, b4 = b3 + k3;
+  const int idx = (lane >= b1) + (lane >= b2) + (lane >= b3);
+  const bool ingrp = lane < b4;
   int img = idx == 0 ? ent.x : (idx == 1 ? ent.y : (idx == 2 ? ent.z : ent.w));
-  if (idx >= ipw) img = -1;
+  if (!ingrp) img = -1;
   const bool valid = img >= 0 && img < P.N;
-  const bool ingrp = idx < ipw;
-  const int gsz = ingrp ? gs : 1;
-  const int gbase = ingrp ? idx * gs : lane;
+  const int gsz = ingrp ? (idx == 0 ? k0 : (idx == 1 ? k1 : (idx == 2 ? k2 : k3))) : 1;
+  const int gbase = ingrp ? (idx == 0 ? 0 : (idx == 1 ? b1 : (idx == 2 ? b2 : b3))) : lane;
   const int slot = lane - gbase;
   const int64_t im = valid ? img : 0;
   const float* psi_in = ws_in + (size_t)im * kWsStride;
@@ -1089,19 +1094,48 @@ hw_row4q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
 }
 
 // counting sort for the packed kernel: bins[0..31] counts, [32..63] first warp of the bin,
-// [64..95] cursors, [96] number of warps
-__global__ void hw_pack_prefix_kernel(int32_t* __restrict__ bins) {
+// [64..95] cursors, [96] number of warps, [97] number of guest records, [kPackOwn + b] images of bin b
+// that stay in the bin's own warps, [kPackRec + 4 r ..] guest record r = (guest bin, images, first host
+// warp, list slot).
+// Guests (mix != 0): a warp of floor(32 / k) images of k lanes leaves 32 mod k lanes idle - 10 of 32 at
+// k = 11, 8 at k = 12.  A warp costs (its longest line) x (its slowest image), so an image with a shorter
+// line rides in those lanes for free: every warp of a bin with a free list slot takes one guest from the
+// largest bin that fits (the guest that is most expensive to run on its own).  Hosts come first in the
+// list, so the first image of a warp has its longest line.  Nothing depends on which images share a warp.
+constexpr int kPackOwn = 4 * kSortBins, kPackRec = 5 * kSortBins, kPackMaxRec = 32;
+constexpr int kPackInts = kPackRec + 4 * kPackMaxRec;
+__global__ void hw_pack_prefix_kernel(int32_t* __restrict__ bins, int mix) {
   if (threadIdx.x == 0) {
-    int start = 0;
+    int rem[kSortBins];
+    for (int b = 0; b < kSortBins; ++b) rem[b] = bins[b];
+    int start = 0, nrec = 0;
     for (int b = kSortBins - 1; b >= 0; --b) {  // longest lines first
-      const int c = bins[b];
+      const int c = rem[b];
       const int gs = b > 1 ? b : 1;
       const int ipw = 32 / gs < 4 ? 32 / gs : 4;
+      const int W = (c + ipw - 1) / ipw;
       bins[kSortBins + b] = start;
       bins[2 * kSortBins + b] = 0;
-      start += (c + ipw - 1) / ipw;
+      bins[kPackOwn + b] = c;
+      if (mix && ipw < 4) {
+        int filled = 0;
+        const int freel = 32 - ipw * gs;
+        for (int g = freel < b - 1 ? freel : b - 1; g >= 2 && filled < W && nrec < kPackMaxRec; --g) {
+          const int n = rem[g] < W - filled ? rem[g] : W - filled;
+          if (n <= 0) continue;
+          int32_t* rec = bins + kPackRec + 4 * nrec++;
+          rec[0] = g;
+          rec[1] = n;
+          rec[2] = start + filled;
+          rec[3] = ipw;
+          rem[g] -= n;
+          filled += n;
+        }
+      }
+      start += W;
     }
     bins[3 * kSortBins] = start;
+    bins[3 * kSortBins + 1] = nrec;
   }
 }
 __global__ void hw_pack_scatter_kernel(const uint8_t* __restrict__ keys, int64_t n, int32_t* __restrict__ bins,
@@ -1125,7 +1159,22 @@ __global__ void hw_pack_scatter_kernel(const uint8_t* __restrict__ keys, int64_t
     const int gs = b > 1 ? b : 1;
     const int ipw = 32 / gs < 4 ? 32 / gs : 4;
     const int pos = base[b] + local;
-    perm4[4 * (bins[kSortBins + b] + pos / ipw) + pos % ipw] = (int32_t)i;
+    const int own = bins[kPackOwn + b];
+    if (pos < own) {
+      perm4[4 * (bins[kSortBins + b] + pos / ipw) + pos % ipw] = (int32_t)i;
+    } else {  // guest: the bin's records in order
+      int q = pos - own;
+      const int nrec = bins[3 * kSortBins + 1];
+      for (int r = 0; r < nrec; ++r) {
+        const int32_t* rec = bins + kPackRec + 4 * r;
+        if (rec[0] != b) continue;
+        if (q < rec[1]) {
+          perm4[4 * (rec[2] + q) + rec[3]] = (int32_t)i;
+          break;
+        }
+        q -= rec[1];
+      }
+    }
   }
 }
 
@@ -1770,6 +1819,10 @@ inline int& pack_step4() {
   static int v = 1;
   return v;
 }
+inline int& mix_step4() {
+  static int v = 1;
+  return v;
+}
 inline int& mgs_step4() {
   static int v = 1;
   return v;
@@ -1816,7 +1869,7 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
     cudaMemsetAsync(perm, 0xff, (size_t)4 * max_warps * sizeof(int32_t), st);
     const int tb = 256, gb = (int)((P.N + tb - 1) / tb);
     hw_sort_hist_kernel<<<gb, tb, 0, st>>>(keys, P.N, bins);
-    hw_pack_prefix_kernel<<<1, 32, 0, st>>>(bins);
+    hw_pack_prefix_kernel<<<1, 32, 0, st>>>(bins, mgs_step4() && mix_step4());
     hw_pack_scatter_kernel<<<gb, tb, 0, st>>>(keys, P.N, bins, perm);
     const int grid4 = (int)((max_warps + kHwWarps - 1) / kHwWarps);
     const size_t smem4p = (size_t)kHwWarps * 64 * 34 * sizeof(float);

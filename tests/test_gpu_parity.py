@@ -423,6 +423,11 @@ def test_two_stream_chunk_split_is_bit_identical(gpu_lib):
     assert torch.equal(ov_new, ov_ref) and torch.equal(am_new, am_ref)
 
 
+def torch_equal(a, b):
+    import torch
+    return bool(torch.equal(a, b))
+
+
 def test_encoding_does_not_depend_on_batch_composition(gpu_lib):
     """Images share warps (two per warp in most kernels, up to four of equal
     live-row count in the packed step 4, chosen by a device-side counting sort
@@ -439,6 +444,17 @@ def test_encoding_does_not_depend_on_batch_composition(gpu_lib):
             np.testing.assert_array_equal(x, y)
     for x, y in zip(full.sites_numpy(5), alone.sites_numpy(0)):
         np.testing.assert_array_equal(x, y)
+    # guests in the packed step 4 (a warp's idle lanes take an image with a shorter line, which then
+    # runs in the longer-vector instantiation of its host): same bits as equal-length warps only
+    from orthogonal_classifiers_b200 import batched
+    many = synthetic_images(3000, seed=29).astype(np.float32)
+    mixed = gpu_lib.encode_images(many, 32, return_svals=True)
+    batched.set_option("enc_mix", 0)
+    try:
+        plain = gpu_lib.encode_images(many, 32, return_svals=True)
+    finally:
+        batched.set_option("enc_mix", 1)
+    assert torch_equal(mixed.data, plain.data) and torch_equal(mixed.svals, plain.svals)
 
 
 def test_scale_invariance_and_low_contrast(gpu_lib):
