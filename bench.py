@@ -435,8 +435,8 @@ def main():
                     "h2d_bytes_per_step": int(N * 784), "d2h_bytes_per_step": int(N * (16 * 4 + 4)),
                     "host_input": "uint8 pixels (the type MNIST ships; the reference divides by 255 on the host, "
                                   "tools.py:25-74, here /255 happens in the encoder's load), pinned",
-                    "api": "oc_classify_host (C ABI, host buffers; 17,500-image chunks, H2D / kernels on two compute "
-                           "streams / D2H pipelined inside the library)", "ms_per_step": e2e_u8_ms / args.steps},
+                    "api": "oc_classify_host (C ABI, host buffers; chunks of 4,000 / 8,000 / 14,000 / 22,000 / 22,000 images, "
+                           "H2D / kernels on four compute streams / D2H pipelined inside the library)", "ms_per_step": e2e_u8_ms / args.steps},
             "e2e_f32": {"value": world * N * args.steps / (e2e_f32_ms * 1e-3), "unit": "images/s",
                         "h2d_bytes_per_step": int(N * 784 * 4), "d2h_bytes_per_step": int(N * (16 * 4 + 4)),
                         "host_input": "float32 pixels, pinned", "api": "oc_classify_host (C ABI, host buffers)",

@@ -92,12 +92,14 @@ const char* oc_last_error(void);
  *                   the left-canonical gauge before the overlap (as oc_encode_batch does) instead of
  *                   contracting the right-canonical MPS the right-to-left sweep leaves (same overlaps)
  *   "enc_events"    see oc_encode_step_ms
- *   "host_chunk" = n  images per pipeline stage of oc_classify_host (0 = default: 17,500 for uint8 and
- *                   8,750 for float pixels; with "host_streams" = 1: 35,000 / 17,500)
- *   "host_streams" = 1  oc_classify_host: all chunks' kernels on the caller's stream (default 2: odd
- *                   chunks on a second, library-owned compute stream, so that the kernels of two
- *                   chunks fill each other's tail waves; results identical)
- *   "host_ramp" = 0 uint8 input, "host_streams" = 1: equal stages instead of the ramp chunk/4, chunk/2, chunk, ...
+ *   "host_chunk" = n  images per pipeline stage of oc_classify_host (0 = default: 22,000 for uint8 and
+ *                   8,750 for float pixels; with "host_streams" = 2: 17,500 / 8,750, = 1: 35,000 / 17,500)
+ *   "host_streams" = 1 | 2 | 4  compute streams of oc_classify_host (default 4: chunk k runs on stream
+ *                   k mod 4 - the caller's stream and three library-owned ones - so that the kernels of
+ *                   several chunks fill each other's tail waves; 1: everything on the caller's stream;
+ *                   results identical)
+ *   "host_ramp" = 0 uint8 input: equal stages instead of the ramp (4 streams: 2/11, 4/11, 7/11 of a chunk, then
+ *                   full chunks - 4,000 / 8,000 / 14,000 / 22,000 ...; 1 stream: chunk/4, chunk/2, chunk, ...)
  *   "host_trace" = 1  oc_classify_host prints a per-chunk timeline to stderr (2: also re-upload the classifier)
  * Unknown keys return OC_E_ARG. */
 int oc_set_option(const char* key, int value);

@@ -109,19 +109,22 @@ struct ClfEntry {  // a re-laid classifier the caller declared immutable (oc_cla
 
 struct HostPipe {  // oc_classify_host: double-buffered H2D | kernels | D2H
   cudaStream_t copy = nullptr, back = nullptr;
-  cudaStream_t comp2 = nullptr;  // second compute stream: odd chunks run here, so that the kernels of two
-                                 // chunks fill each other's tail waves (own context: own encoder scratch)
-  static constexpr int NB = 4;   // staging buffers: with two compute streams two chunks are in their kernels while
-                                 // the copies of the next two arrive (two buffers left the second pair waiting)
+  static constexpr int NS = 4;   // compute streams: chunk k runs on stream k mod host_streams, so that the kernels
+                                 // of several chunks fill each other's tail waves; [0] is the caller's stream,
+                                 // the others are library-owned (own context: own encoder scratch)
+  cudaStream_t comp[NS] = {};
+  static constexpr int NB = 8;   // staging buffers (a multiple of every stream count): while host_streams chunks
+                                 // are in their kernels the copies of the next ones arrive
   cudaEvent_t copied[NB] = {}, freed[NB] = {}, done[NB] = {}, backdone[NB] = {}, fork = nullptr;
-  Scratch stage[NB], ov[NB], am[NB], clf, mps, mps2;
+  Scratch stage[NB], ov[NB], am[NB], clf, mps[NS];
   void* clf_pin = nullptr;  // pinned staging of the packed classifier (the caller's copy is pageable)
   size_t clf_pin_cap = 0;
   size_t clf_bytes = 0;     // what `clf` holds: the upload is skipped while the caller's classifier is unchanged
   uint64_t clf_hash = 0;
   HostPipe() {
     for (int b = 0; b < NB; ++b) stage[b].async = ov[b].async = am[b].async = false;
-    clf.async = mps.async = mps2.async = false;
+    clf.async = false;
+    for (int i = 0; i < NS; ++i) mps[i].async = false;
   }
 };
 
@@ -142,7 +145,7 @@ int g_fused_sweep = 1;  // oc_encode_classify / oc_classify_host, OC_TRUNC_SWEEP
 int g_host_chunk = 0;  // 0 = default per input type
 int g_host_ramp = 1;
 int g_host_trace = 0;  // 1: oc_classify_host prints a per-chunk timeline (diagnostics)
-int g_host_streams = 2;  // compute streams of oc_classify_host (1 or 2)
+int g_host_streams = 4;  // compute streams of oc_classify_host (1, 2 or 4)
 
 Ctx& get_ctx(cudaStream_t st) {
   int dev = 0;
@@ -173,18 +176,20 @@ void release_ctx(Ctx& cx) {
     }
   }
   hp.clf.release(st);
-  hp.mps.release(st);
-  hp.mps2.release(st);
+  for (int i = 0; i < HostPipe::NS; ++i) hp.mps[i].release(st);
   if (hp.copy) cudaStreamDestroy(hp.copy);
   if (hp.back) cudaStreamDestroy(hp.back);
-  if (hp.comp2) cudaStreamDestroy(hp.comp2);  // (its own context, keyed by the stream, is released by oc_release)
+  for (int i = 1; i < HostPipe::NS; ++i) {  // (their own contexts, keyed by the stream, are released by oc_release)
+    if (hp.comp[i]) cudaStreamDestroy(hp.comp[i]);
+    hp.comp[i] = nullptr;
+  }
   if (hp.fork) cudaEventDestroy(hp.fork);
   if (hp.clf_pin) cudaFreeHost(hp.clf_pin);
   hp.clf_pin = nullptr;
   hp.clf_pin_cap = 0;
   hp.clf_bytes = 0;
   hp.clf_hash = 0;
-  hp.copy = hp.back = hp.comp2 = nullptr;
+  hp.copy = hp.back = nullptr;
   hp.fork = nullptr;
   if (cx.split.aux) cudaStreamDestroy(cx.split.aux);
   if (cx.split.fork) cudaEventDestroy(cx.split.fork);
@@ -553,7 +558,7 @@ int oc_set_option(const char* key, int value) {
     g_host_chunk = value;
     return OC_OK;
   }
-  if (key && !strcmp(key, "host_streams") && (value == 1 || value == 2)) {
+  if (key && !strcmp(key, "host_streams") && (value == 1 || value == 2 || value == 4)) {
     g_host_streams = value;
     return OC_OK;
   }
@@ -866,17 +871,18 @@ int oc_release(void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   Ctx& cx = get_ctx(st);
   std::lock_guard<std::mutex> lk(cx.mu);
-  if (cx.hp.comp2) {  // the context of oc_classify_host's second compute stream goes with its owner
-    Ctx& cx2 = get_ctx(cx.hp.comp2);
+  for (int i = 1; i < HostPipe::NS; ++i) {  // the contexts of oc_classify_host's own compute streams go with their owner
+    if (!cx.hp.comp[i]) continue;
+    Ctx& cxi = get_ctx(cx.hp.comp[i]);
     {
-      std::lock_guard<std::mutex> lk2(cx2.mu);
-      cudaStreamSynchronize(cx.hp.comp2);
-      release_ctx(cx2);
+      std::lock_guard<std::mutex> lki(cxi.mu);
+      cudaStreamSynchronize(cx.hp.comp[i]);
+      release_ctx(cxi);
     }
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lkm(g_ctx_mu);
-    g_ctx.erase({dev, (void*)cx.hp.comp2});
+    g_ctx.erase({dev, (void*)cx.hp.comp[i]});
   }
   release_ctx(cx);
   return OC_OK;
@@ -969,7 +975,7 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
   if (!hp.copy) {
     OC_CUDA(cudaStreamCreateWithFlags(&hp.copy, cudaStreamNonBlocking));
     OC_CUDA(cudaStreamCreateWithFlags(&hp.back, cudaStreamNonBlocking));
-    OC_CUDA(cudaStreamCreateWithFlags(&hp.comp2, cudaStreamNonBlocking));
+    for (int i = 1; i < HostPipe::NS; ++i) OC_CUDA(cudaStreamCreateWithFlags(&hp.comp[i], cudaStreamNonBlocking));
     for (int b = 0; b < HostPipe::NB; ++b)
       for (cudaEvent_t* ev : {&hp.copied[b], &hp.freed[b], &hp.done[b], &hp.backdone[b]})
         OC_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
@@ -978,10 +984,15 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
   // Two compute streams: even chunks on the caller's stream, odd chunks on comp2 (a Jacobi CTA lives
   // 100-200 us whatever the grid, so the last wave of every kernel of a chunk leaves SMs idle; the other
   // chunk's kernels fill them: 17,500-image chunks 3.69 -> 3.27 ms per 70,000 images).
-  const bool two = g_host_streams >= 2;
-  Ctx& cx2 = two ? get_ctx(hp.comp2) : cx;
-  std::unique_lock<std::mutex> lk2;
-  if (two) lk2 = std::unique_lock<std::mutex>(cx2.mu);
+  const int ns = g_host_streams;  // 1, 2 or 4
+  const bool two = ns >= 2;
+  hp.comp[0] = st;
+  Ctx* cxs_[HostPipe::NS] = {&cx, &cx, &cx, &cx};
+  std::unique_lock<std::mutex> lks[HostPipe::NS];
+  for (int i = 1; i < ns; ++i) {
+    cxs_[i] = &get_ctx(hp.comp[i]);
+    lks[i] = std::unique_lock<std::mutex>(cxs_[i]->mu);
+  }
   // chunk schedule: the copy of chunk k + 1 runs under the kernels of chunk k.  Defaults measured on
   // B200; oc_set_option("host_chunk", n) overrides.  When the kernels, not the copy,
   // bound the pipeline (uint8 pixels: 0.75 KB per image) the schedule ramps up - chunk / 4, chunk / 2,
@@ -989,7 +1000,12 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
   // measured defaults (70,000 images, scripts/e2e_streams.py): two compute streams - 17,500 for uint8 pixels
   // (kernel-bound: 3.86 ms), 8,750 for float pixels (copy-bound: a short last chunk, 4.73 ms); one stream -
   // 35,000 with the ramp / 17,500
-  const int64_t dflt = two ? (in_dtype == OC_U8 ? 17500 : 8750) : (in_dtype == OC_U8 ? 35000 : 17500);
+  // four compute streams (default; scripts/e2e_plans4.py): uint8 - 22,000 behind the ramp 4,000 / 8,000 / 14,000 (the
+  // first kernels start 0.06 ms into the call instead of 0.26 ms, and the short chunks' kernels, which would idle most
+  // SMs on their own, run beside their successors': 3.69 ms against 3.79 ms with two streams and equal chunks);
+  // float - 8,750 as with two streams (copy-bound either way)
+  const int64_t dflt = ns >= 4 ? (in_dtype == OC_U8 ? 22000 : 8750)
+                               : (two ? (in_dtype == OC_U8 ? 17500 : 8750) : (in_dtype == OC_U8 ? 35000 : 17500));
   const int64_t base = std::min<int64_t>(g_host_chunk > 0 ? g_host_chunk : dflt, N);
   std::vector<int64_t> sizes;
   if (const char* plan = getenv("OC_HOST_SIZES")) {  // diagnostics: explicit chunk sizes, e.g. "17500,17500,35000"
@@ -1013,6 +1029,13 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
           left -= c;
         }
       }
+    } else if (in_dtype == OC_U8 && g_host_ramp && ns >= 4 && base >= 11000) {
+      for (int64_t c : {base * 2 / 11, base * 4 / 11, base * 7 / 11}) {
+        if (left > c + base / 2) {
+          sizes.push_back(c);
+          left -= c;
+        }
+      }
     }
     while (left > 0) {
       int64_t c = std::min(base, left);
@@ -1030,9 +1053,8 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
   }
   if ((size_t)clf_elems * esz > hp.clf.cap) hp.clf_bytes = 0;  // a new buffer: the cached upload is gone
   if (int rc = hp.clf.ensure((size_t)clf_elems * esz, st)) return rc;
-  if (int rc = hp.mps.ensure((size_t)chunk * offs[L] * esz, st)) return rc;
-  if (two && sizes.size() > 1)
-    if (int rc = hp.mps2.ensure((size_t)chunk * offs[L] * esz, st)) return rc;
+  for (int i = 0; i < ns && i < (int)sizes.size(); ++i)
+    if (int rc = hp.mps[i].ensure((size_t)chunk * offs[L] * esz, st)) return rc;
   // The classifier goes up through a pinned staging buffer: a copy from the caller's pageable array is
   // serviced by the copy engine only after the image copies queued behind it (measured: the first chunk's
   // kernels started when the SECOND chunk's copy had finished, 0.26 ms late).  The previous call ended with a
@@ -1061,9 +1083,9 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
       hp.clf_hash = h;
     }
   }
-  if (two) {  // comp2 joins the caller's stream order: after the classifier upload and everything before the call
+  if (two) {  // the library's streams join the caller's stream order: after the classifier upload and everything before the call
     OC_CUDA(cudaEventRecord(hp.fork, st));
-    OC_CUDA(cudaStreamWaitEvent(hp.comp2, hp.fork, 0));
+    for (int i = 1; i < ns; ++i) OC_CUDA(cudaStreamWaitEvent(hp.comp[i], hp.fork, 0));
   }
   // diagnostics ("host_trace"): timing events around every stage of every chunk
   std::vector<cudaEvent_t> tr;
@@ -1083,10 +1105,10 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
   for (; k < (int)sizes.size(); lo += sizes[k], ++k) {
     const int64_t n = sizes[k];
     const int b = k % NB;                               // chunk k and k + NB share the buffers [b] ...
-    const bool odd = two && (k & 1);                    // ... and (NB even) the compute stream
-    cudaStream_t cs = odd ? hp.comp2 : st;
-    Ctx& cxs = odd ? cx2 : cx;
-    void* mps_ws = odd ? hp.mps2.p : hp.mps.p;
+    const int si = k % ns;                              // ... and (NB a multiple of ns) the compute stream
+    cudaStream_t cs = hp.comp[si];
+    Ctx& cxs = *cxs_[si];
+    void* mps_ws = hp.mps[si].p;
     // rows lo .. lo + n - 1: the last row ends after n_pix elements, not after ld
     const size_t in_bytes = ((size_t)(n - 1) * ld + n_pix) * isz;
     if (k >= NB) OC_CUDA(cudaStreamWaitEvent(hp.copy, hp.freed[b], 0));  // chunk k - NB is done with stage[b]
