@@ -325,6 +325,8 @@ __device__ __forceinline__ int pivoted_cholesky(const double* __restrict__ g, do
 // One-sided Jacobi (odd-even ordering) on the 2 * gsz vectors of each lane
 // group [gbase, gbase + gsz), 16 elements per vector, groups of different size
 // side by side.  Same rotation kernel and stopping rule as hw::jacobi16.
+// NEJ packed pairs per vector take part (7 when rows 14, 15 of X_3 are padding: n_pix <= 896).
+template <int NEJ>
 __device__ __forceinline__ int jacobi_groups(u64 (&T)[16], u64 (&S)[16], float& nT, float& nS, float thr2,
                                              int lane, int gsz, int gbase, int mlive, int mlive_max) {
   const int slot = lane - gbase;
@@ -339,7 +341,7 @@ __device__ __forceinline__ int jacobi_groups(u64 (&T)[16], u64 (&S)[16], float& 
     bool again = false;
     bool lostf = false;
     {
-      const float fT = dot16<0, 8>(T, T), fS = dot16<0, 8>(S, S);
+      const float fT = dot16<0, NEJ>(T, T), fS = dot16<0, NEJ>(S, S);
       if (!done) {
         nT = fT;
         nS = fS;
@@ -348,13 +350,13 @@ __device__ __forceinline__ int jacobi_groups(u64 (&T)[16], u64 (&S)[16], float& 
 #pragma unroll 1
     for (int rr = 0; rr < mlive_max; ++rr) {
       const bool off = done || rr >= mlive;
-      rotate16<0, 8>(T, S, nT, nS, thr2, off, lostf, again);
+      rotate16<0, NEJ>(T, S, nT, nS, thr2, off, lostf, again);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) T[e] = shfl2(T[e], src_dn);
+      for (int e = 0; e < NEJ; ++e) T[e] = shfl2(T[e], src_dn);
       float nR = __shfl_sync(FULL, nT, src_dn);
-      rotate16<0, 8>(S, T, nS, nR, thr2, off || idleB, lostf, again);
+      rotate16<0, NEJ, true>(S, T, nS, nR, thr2, off || idleB, lostf, again);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) T[e] = shfl2(T[e], src_up);
+      for (int e = 0; e < NEJ; ++e) T[e] = shfl2(T[e], src_up);
       nT = __shfl_sync(FULL, nR, src_up);
       {
 #ifdef OC_TRACK_LOST
@@ -363,7 +365,7 @@ __device__ __forceinline__ int jacobi_groups(u64 (&T)[16], u64 (&S)[16], float& 
         const unsigned lostmask = 0u;
 #endif
         if (lostmask) {
-          const float fT = dot16<0, 8>(T, T), fS = dot16<0, 8>(S, S);
+          const float fT = dot16<0, NEJ>(T, T), fS = dot16<0, NEJ>(S, S);
           if (lostmask & gmask) {
             nT = fT;
             nS = fS;
@@ -381,7 +383,7 @@ __device__ __forceinline__ int jacobi_groups(u64 (&T)[16], u64 (&S)[16], float& 
 }
 
 // ---- K1b: steps 0..3 from G_3; Psi_4 to the workspace ----
-template <int MODE>
+template <int MODE, int NEJ>
 __global__ void __launch_bounds__(kHwWarps * 32, 4)
 gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restrict__ g_in,
                  float* __restrict__ ws_out, uint8_t* __restrict__ keys) {
@@ -479,7 +481,7 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
   for (int o = 16; o > 0; o >>= 1) mlive_max = max(mlive_max, __shfl_xor_sync(FULL, mlive_max, o));
   int sweeps = 0;
   if (mlive_max > 0) {
-    sweeps = jacobi_groups(T, S, nT, nS, thr2, lane, gsz, gbase, mlive, mlive_max);
+    sweeps = jacobi_groups<NEJ>(T, S, nT, nS, thr2, lane, gsz, gbase, mlive, mlive_max);
     nT = dot16<0, 8>(T, T);
     nS = dot16<0, 8>(S, S);
   }
@@ -508,11 +510,13 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
     }
     if (io.sweeps && slot == 0) *io.sweeps = sweeps;
   }
+  int kept_max;  // of the warp's two images: columns >= kept of U^(3) are zero, the rows of Psi_4 behind them too
   {
     // kept vectors of problem 3 = non-zero rows of Psi_4 (pairing key of step 4)
     const unsigned kt = __ballot_sync(FULL, kT && nJ == 3), ks = __ballot_sync(FULL, kS && nJ == 3);
     const int kept = __popc((kt >> hb) & 0xffu) + __popc((ks >> hb) & 0xffu);
     if (keys && valid && l16 == 0) keys[im] = (uint8_t)kept;
+    kept_max = max(__popc(kt & 0xffu) + __popc(ks & 0xffu), __popc((kt >> 16) & 0xffu) + __popc((ks >> 16) & 0xffu));
   }
   // ---- U^(n)[row][rank] -> shared: Uf [rank][row] (stride p + 1); U^(3) also transposed ----
   if (l16 != 15) {
@@ -627,6 +631,7 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
         const float xv[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
 #pragma unroll
         for (int l4 = 0; l4 < 4; ++l4) {
+          if (4 * l4 >= kept_max) continue;  // warp-uniform: zero columns of U^(3) (13 live rows: rank <= 13)
           const float4 u = *reinterpret_cast<const float4*>(Ut + (i0 + j) * 16 + 4 * l4);
           const float uv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -667,12 +672,16 @@ inline cudaError_t launch_head(const EncodeParams& P, double* gws, float* ws_psi
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(gram_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
       if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(gram_head_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+      e = cudaFuncSetAttribute(gram_head_kernel<MODE, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(gram_head_kernel<MODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
     gram_kernel<MODE><<<grid, kHwWarps * 32, smem_a, st>>>(P, gws);
-    gram_head_kernel<MODE><<<grid, kHwWarps * 32, smem_b, st>>>(P, gws, ws_psi4, keys);
+    // rows 14 and 15 of X_3 (pixels 896..1023) are padding for MNIST-shaped images: the L columns end there
+    if (P.n_pix <= 896) gram_head_kernel<MODE, 7><<<grid, kHwWarps * 32, smem_b, st>>>(P, gws, ws_psi4, keys);
+    else gram_head_kernel<MODE, 8><<<grid, kHwWarps * 32, smem_b, st>>>(P, gws, ws_psi4, keys);
     return cudaGetLastError();
   };
   if (mode == 0) return launch(std::integral_constant<int, 0>{});

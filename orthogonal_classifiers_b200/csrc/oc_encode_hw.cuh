@@ -73,7 +73,12 @@ __device__ __forceinline__ float dot16(const u64 (&a)[NA], const u64 (&b)[NB]) {
 // ends in round B, and everything a finished / shorter half-warp still has to
 // sit through while its partner image works, so that the result for an image
 // never depends on which image shares its warp.
-template <int LOGLP, int NE = 16, int NA>
+// KEEPA picks which products are formed first, i.e. whose registers the results can reuse: false - a' is
+// built on c*y in fresh registers and b' overwrites y (right when a moves on by shuffle and b stays: round
+// A); true - a' overwrites x and b' is built on c*x in fresh registers (round B: a stays, b is shuffled
+// back).  With one form for both, ptxas ended every round pair with ~2 NE register moves (17 % of the
+// loop's instructions at NE = 13).
+template <int LOGLP, int NE = 16, bool KEEPA = false, int NA>
 __device__ __forceinline__ void rotate16(u64 (&a)[NA], u64 (&b)[NA], float& na, float& nb, float thr2,
                                          bool hold, bool& lostf, bool& again) {
   const float ab = dot16<LOGLP, NE>(a, b);
@@ -112,8 +117,13 @@ __device__ __forceinline__ void rotate16(u64 (&a)[NA], u64 (&b)[NA], float& na, 
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
     const u64 x = a[e], y = b[e];
-    a[e] = fma2(s2, x, mul2(c2, y));
-    b[e] = fma2(c2, x, mul2(ns2, y));
+    if constexpr (KEEPA) {
+      b[e] = fma2(ns2, y, mul2(c2, x));
+      a[e] = fma2(c2, y, mul2(s2, x));
+    } else {
+      a[e] = fma2(s2, x, mul2(c2, y));
+      b[e] = fma2(c2, x, mul2(ns2, y));
+    }
   }
   na = n_first;
   nb = n_second;
@@ -155,7 +165,7 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
 #pragma unroll
         for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_dn);
         float nR = __shfl_sync(FULL, nT, src_dn);
-        rotate16<LOGLP, NE>(S, T, nS, nR, thr2, off || idleB, lostf, again);
+        rotate16<LOGLP, NE, true>(S, T, nS, nR, thr2, off || idleB, lostf, again);
 #pragma unroll
         for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_up);
         nT = __shfl_sync(FULL, nR, src_up);
@@ -615,7 +625,7 @@ __device__ __forceinline__ int jacobi_ring(u64 (&T)[NA], u64 (&S)[NA], float& nT
 #pragma unroll
       for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_dn);
       float nR = __shfl_sync(FULL, nT, src_dn);
-      rotate16<0, NE>(S, T, nS, nR, thr2, off || idleB, lostf, again);
+      rotate16<0, NE, true>(S, T, nS, nR, thr2, off || idleB, lostf, again);
 #pragma unroll
       for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_up);
       nT = __shfl_sync(FULL, nR, src_up);
@@ -1610,7 +1620,28 @@ hw_col5q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
     sS += __shfl_xor_sync(FULL, sS, 1);
     const float jT = keyT > 0.f ? rsqrtf(sT) : 0.f;
     const float jS = keyS > 0.f ? rsqrtf(sS) : 0.f;
-    if (valid) {
+    if (valid && b_rt == 32 && r_rt == Q && (reinterpret_cast<uintptr_t>(io.A) & 15) == 0) {
+      // D >= 32 (the untruncated site, 2 x 32 x 16): no bounds to test, the structurally zero rows
+      // l >= 2 NE of both s as 128-bit stores (the run-time-shaped code below was 28 % of this kernel's samples)
+      float* A = io.A + sub * 32 * Q;
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        float t0, t1, s0, s1;
+        unpack2(UT[j], t0, t1);
+        unpack2(US[j], s0, s1);
+        A[(2 * j) * Q + tagT] = t0 * jT;
+        A[(2 * j) * Q + tagS] = s0 * jS;
+        A[(2 * j + 1) * Q + tagT] = t1 * jT;
+        A[(2 * j + 1) * Q + tagS] = s1 * jS;
+      }
+      constexpr int Z4 = (32 - 2 * NE) * Q / 4;  // float4 per s
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (Z4 > 0) {
+#pragma unroll
+        for (int q = lg; q < 2 * Z4; q += 16)
+          *reinterpret_cast<float4*>(io.A + ((q / Z4) * 32 + 2 * NE) * Q + 4 * (q % Z4)) = z;
+      }
+    } else if (valid) {
 #pragma unroll
       for (int j = 0; j < NE; ++j) {
         float t0, t1, s0, s1;
