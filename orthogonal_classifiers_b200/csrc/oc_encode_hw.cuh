@@ -200,7 +200,7 @@ __device__ __forceinline__ int jacobi16(u64 (&T)[16], u64 (&S)[16], float& nT, f
 // singular value (key) is orthogonalised against the other; nothing else
 // changes, so the well-determined columns keep their accuracy.  Keys and rank
 // tags travel with the columns (positions swap as in the Jacobi ordering).
-template <int LOGLP, int B2, bool SPREAD = false>
+template <int LOGLP, int B2, bool SPREAD = false, bool KEEPA = false>
 __device__ __forceinline__ void polish_pair(u64 (&a)[B2], u64 (&b)[B2], float& ka, float& kb, int& ra, int& rb,
                                             bool hold) {
   u64 acc0 = mul2(a[0], b[0]), acc1 = 0ull;
@@ -224,8 +224,13 @@ __device__ __forceinline__ void polish_pair(u64 (&a)[B2], u64 (&b)[B2], float& k
 #pragma unroll
   for (int e = 0; e < B2; ++e) {
     const u64 x = a[e], y = b[e];
-    a[e] = fma2(s2, x, mul2(c2, y));
-    b[e] = fma2(c2, x, mul2(ns2, y));
+    if constexpr (KEEPA) {  // see rotate16
+      b[e] = fma2(ns2, y, mul2(c2, x));
+      a[e] = fma2(c2, y, mul2(s2, x));
+    } else {
+      a[e] = fma2(s2, x, mul2(c2, y));
+      b[e] = fma2(c2, x, mul2(ns2, y));
+    }
   }
   if (!hold) {
     const float k = ka;
@@ -256,7 +261,7 @@ __device__ __forceinline__ void polish16(u64 (&T)[B2], u64 (&S)[B2], float& kT, 
       for (int e = 0; e < B2; ++e) T[e] = shfl2(T[e], src_dn);
       float kR = __shfl_sync(FULL, kT, src_dn);
       int rR = __shfl_sync(FULL, rT, src_dn);
-      polish_pair<LOGLP, B2, SPREAD>(S, T, kS, kR, rS, rR, off || idleB);
+      polish_pair<LOGLP, B2, SPREAD, true>(S, T, kS, kR, rS, rR, off || idleB);
 #pragma unroll
       for (int e = 0; e < B2; ++e) T[e] = shfl2(T[e], src_up);
       kT = __shfl_sync(FULL, kR, src_up);
@@ -669,7 +674,7 @@ __device__ __forceinline__ void polish_ring(u64 (&T)[B2], u64 (&S)[B2], float& k
     for (int e = 0; e < B2; ++e) T[e] = shfl2(T[e], src_dn);
     float kR = __shfl_sync(FULL, kT, src_dn);
     int rR = __shfl_sync(FULL, rT, src_dn);
-    polish_pair<0, B2>(S, T, kS, kR, rS, rR, off || idleB);
+    polish_pair<0, B2, false, true>(S, T, kS, kR, rS, rR, off || idleB);
 #pragma unroll
     for (int e = 0; e < B2; ++e) T[e] = shfl2(T[e], src_up);
     kT = __shfl_sync(FULL, kR, src_up);
