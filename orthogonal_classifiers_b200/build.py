@@ -25,8 +25,22 @@ def _sources():
     return out
 
 
+FLAGS_FILE = os.path.join(PKG, "liboc_b200.flags")   # the flags the library next to it was built with (travels with the .so)
+
+
+def _flags_key() -> str:
+    return " ".join(NVCC_FLAGS + os.environ.get("OC_NVCC_EXTRA", "").split())
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
+        return True
+    # an experimental build (OC_NVCC_EXTRA=-D...) must not stay in place as the shipped library
+    try:
+        with open(FLAGS_FILE) as f:
+            if f.read().strip() != _flags_key():
+                return True
+    except OSError:
         return True
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(s) > t for s in _sources())
@@ -51,6 +65,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    with open(FLAGS_FILE, "w") as f:
+        f.write(_flags_key() + "\n")
     return LIB
 
 
