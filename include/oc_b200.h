@@ -71,6 +71,8 @@ const char* oc_last_error(void);
  *   "enc_gram" = 0  steps 0-3 by Jacobi on the image unfoldings instead of the
  *                   16 x 16 Gram matrix
  *   "enc_pack" = 0  step 4 with 16 lanes per image instead of packed warps
+ *   "enc_u8mma" = 0  uint8 pixels: G_3 = X_3 X_3^T through fp64 FMAs like float pixels (default 1: the exact
+ *                   integer Gram matrix on the tensor cores, mma.sync u8 x u8 -> s32)
  *   "enc_mix"  = 0  packed step 4: only images with equally long lines share a warp (default 1: the
  *                   idle lanes of a warp also take one image with a shorter line; bit-identical results)
  *   "enc_mgs4" = 0  step 4 without the Gram-Schmidt preconditioning

@@ -623,6 +623,10 @@ int oc_set_option(const char* key, int value) {
     oc::hw::pack_step4() = value;
     return OC_OK;
   }
+  if (key && !strcmp(key, "enc_u8mma")) {
+    oc::gram::u8_imma() = value;
+    return OC_OK;
+  }
   if (key && !strcmp(key, "enc_mix")) {
     oc::hw::mix_step4() = value;
     return OC_OK;

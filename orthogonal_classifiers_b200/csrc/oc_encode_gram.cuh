@@ -23,6 +23,7 @@
 // half-warp (lanes 0-7 | 8-11 | 12-13 | 14).  Psi_4 = U^(3)^T X_3 goes to the
 // global workspace for the step-4 kernel, as before.
 #pragma once
+#include <algorithm>
 #include <type_traits>
 #include "oc_encode_hw.cuh"
 
@@ -40,14 +41,12 @@ constexpr double kCholFloor = 1e-13;  // pivots below this fraction of trace(G) 
 
 // ---- pixels: four consecutive amplitudes i .. i+3 of the tail-padded image ----
 struct PixRow {
-  const float* lut;  // MODE 2: 256 floats k / 255.f in shared memory (else unused)
   const void* p;
   int dtype, n_pix;
   bool vec, vec8;
 };
 __device__ __forceinline__ PixRow pix_row(const EncodeParams& P, int64_t img) {
   PixRow r;
-  r.lut = nullptr;
   const char* src = reinterpret_cast<const char*>(P.images);
   const int esz = P.in_dtype == 0 ? 4 : (P.in_dtype == 1 ? 8 : 1);
   r.p = src + (size_t)img * P.ld * esz;
@@ -73,6 +72,16 @@ __device__ __forceinline__ float4 pix4(const PixRow& r, int i) {
   return v;
 }
 
+// byte J of w as the amplitude k / 255.f, the same bits as float(k) / 255.f (checked for all 256 k) without
+// I2F, division or a table in shared memory (the table's loads were 13 % of the head kernel's samples):
+// 0x4B000000 | k is the float 2^23 + k; q = k * (1/255) is corrected once with the exact remainder.
+template <int J>
+__device__ __forceinline__ float byte_amp(unsigned w) {
+  const float f = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | J)) - 8388608.f;
+  const float r = 1.f / 255.f;
+  const float q = f * r;
+  return fmaf(fmaf(-q, 255.f, f), r, q);
+}
 // MODE 0: fp32 rows, 16-byte aligned quads, n_pix % 4 == 0 -> one predicated LDG.128, no branches
 // (so that the loads of a whole image can be in flight together); MODE 2: the same for u8;
 // MODE -1: anything else (per-pixel loads).
@@ -83,26 +92,39 @@ __device__ __forceinline__ float4 pix4m(const PixRow& r, int i) {
     if (i < r.n_pix) v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r.p) + i));
     return v;
   } else if constexpr (MODE == 2) {
-    // table lookup instead of four I2F + fp32 divisions (same bits: the table holds float(k) / 255.f)
-    uchar4 u = make_uchar4(0, 0, 0, 0);
-    if (i < r.n_pix) u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(r.p) + i));
-    if (r.lut) return make_float4(r.lut[u.x], r.lut[u.y], r.lut[u.z], r.lut[u.w]);
-    return make_float4(float(u.x) / 255.f, float(u.y) / 255.f, float(u.z) / 255.f, float(u.w) / 255.f);
+    unsigned w = 0u;
+    if (i < r.n_pix) w = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const uint8_t*>(r.p) + i));
+    return make_float4(byte_amp<0>(w), byte_amp<1>(w), byte_amp<2>(w), byte_amp<3>(w));
   } else {
     return pix4(r, i);
   }
 }
-// fills the k / 255.f table of a CTA (all threads call it; MODE 2 only)
+// The same in two halves, so that a prefetched quad can wait in registers in its raw form (one word for
+// uint8) and is converted where it is used, not where it is loaded (the conversion would wait for the load).
 template <int MODE>
-__device__ __forceinline__ const float* pix_lut() {
+struct RawQuad {
+  using type = float4;
+};
+template <>
+struct RawQuad<2> {
+  using type = unsigned;
+};
+template <int MODE>
+__device__ __forceinline__ typename RawQuad<MODE>::type pix4raw(const PixRow& r, int i, bool on) {
   if constexpr (MODE == 2) {
-    __shared__ float lut[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = float(i) / 255.f;
-    __syncthreads();
-    return lut;
+    unsigned w = 0u;
+    if (on && i < r.n_pix) w = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const uint8_t*>(r.p) + i));
+    return w;
   } else {
-    return nullptr;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) v = pix4m<MODE>(r, i);
+    return v;
   }
+}
+template <int MODE>
+__device__ __forceinline__ float4 pix4cvt(typename RawQuad<MODE>::type raw) {
+  if constexpr (MODE == 2) return make_float4(byte_amp<0>(raw), byte_amp<1>(raw), byte_amp<2>(raw), byte_amp<3>(raw));
+  else return raw;
 }
 inline int pix_mode(const EncodeParams& P) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(P.images);
@@ -138,11 +160,9 @@ __global__ void __launch_bounds__(kHwWarps * 32, 3) gram_kernel(const __grid_con
   const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * 2 + h;
   const bool valid = img < P.N;
   double* Xt = smem_d + (size_t)(warp * 2 + h) * kXtDoubles;
-  const float* lut = pix_lut<MODE>();
   // stage: coalesced loads (all 16 in flight), then fp64 stores Xt[k][row]
   {
     PixRow src = pix_row(P, valid ? img : 0);
-    src.lut = lut;
     float4 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -241,6 +261,64 @@ __global__ void __launch_bounds__(kHwWarps * 32, 3) gram_kernel(const __grid_con
       g[(4 * ib2 + b) * 16 + ra] = f2[b];
     }
   }
+}
+
+// ---- K1a for uint8 pixels: G_3 = X_3 X_3^T as an EXACT integer Gram matrix on the tensor cores ----
+// Pixels k = 0..255 (the amplitude is k / 255): a product is < 2^16 and a sum of 64 of them < 2^22, so
+// G_3 * 255^2 is an integer that mma.sync.m16n8k32.u8.u8.s32 (SASS IMMA.16832) accumulates exactly - no
+// fp64 staging, no DFMA: the kernel is a stream over the pixels.  One image per warp and pass: lane
+// (g, t) = (lane / 4, lane % 4) loads the 16 bytes 16 t .. 16 t + 15 of rows g and g + 8 of X_3 (16 rows
+// of 64 pixels), the whole 1 KB image in two 128-bit loads per lane.  G = sum_k X[m][k] X[n][k] does not
+// care in which order k is summed, so the lane's four words serve as the k-slots 4 t .. 4 t + 3 of four
+// k-blocks (two per MMA), and since B[k][n] = X[n][k] the B fragments ARE the A registers of rows g
+// (columns 0-7 of G) and g + 8 (columns 8-15).  Four MMAs per image; the accumulators (rows g, g + 8,
+// columns 2 t, 2 t + 1 of both column blocks) go out as fp64 / 255^2, 16 bytes per store.
+// Needs 16-byte aligned rows (ld and n_pix multiples of 16: 784 and 1024 are); otherwise gram_kernel<2>.
+__device__ __forceinline__ void imma_u8(int (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                        unsigned b1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+constexpr int kGramU8Unroll = 4;  // images in flight per warp
+__global__ void __launch_bounds__(256) gram_u8_kernel(const __grid_constant__ EncodeParams P, double* __restrict__ g_out) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint8_t* images = reinterpret_cast<const uint8_t*>(P.images);
+  const int o0 = 64 * g + 16 * t, o1 = o0 + 512;
+  const bool in0 = o0 < P.n_pix, in1 = o1 < P.n_pix;  // n_pix % 16 == 0: a 16-byte piece is inside or padding
+  const double sc = 1.0 / 65025.0;
+  for (int64_t i0 = warp * kGramU8Unroll; i0 < P.N; i0 += nwarps * kGramU8Unroll) {
+    uint4 r0[kGramU8Unroll], r1[kGramU8Unroll];
+#pragma unroll
+    for (int u = 0; u < kGramU8Unroll; ++u) {
+      r0[u] = r1[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i0 + u < P.N) {
+        const uint8_t* src = images + (size_t)(i0 + u) * P.ld;
+        if (in0) r0[u] = __ldcs(reinterpret_cast<const uint4*>(src + o0));
+        if (in1) r1[u] = __ldcs(reinterpret_cast<const uint4*>(src + o1));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGramU8Unroll; ++u) {
+      if (i0 + u >= P.N) break;
+      int c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};
+      imma_u8(c0, r0[u].x, r1[u].x, r0[u].y, r1[u].y, r0[u].x, r0[u].y);
+      imma_u8(c1, r0[u].x, r1[u].x, r0[u].y, r1[u].y, r1[u].x, r1[u].y);
+      imma_u8(c0, r0[u].z, r1[u].z, r0[u].w, r1[u].w, r0[u].z, r0[u].w);
+      imma_u8(c1, r0[u].z, r1[u].z, r0[u].w, r1[u].w, r1[u].z, r1[u].w);
+      double* G = g_out + (size_t)(i0 + u) * kGStride;
+      *reinterpret_cast<double2*>(G + g * 16 + 2 * t) = make_double2(c0[0] * sc, c0[1] * sc);
+      *reinterpret_cast<double2*>(G + (g + 8) * 16 + 2 * t) = make_double2(c0[2] * sc, c0[3] * sc);
+      *reinterpret_cast<double2*>(G + g * 16 + 8 + 2 * t) = make_double2(c1[0] * sc, c1[1] * sc);
+      *reinterpret_cast<double2*>(G + (g + 8) * 16 + 8 + 2 * t) = make_double2(c1[2] * sc, c1[3] * sc);
+    }
+  }
+}
+inline int& u8_imma() {
+  static int v = 1;
+  return v;
 }
 
 // ---- shared-memory map of one image in K1b ----
@@ -543,24 +621,10 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
 
   // first rows of X_3 for the Psi_4 product: in flight during the A_n products
   PixRow src = pix_row(P, im);
-  if constexpr (MODE == 2) {
-    // k / 255.f table of this WARP in the (now dead) fp32 L-column buffer of its first image:
-    // 1 KB more of CTA-wide shared memory would cost the fourth CTA per SM
-    float* lutw = reinterpret_cast<float*>(smem_b + (size_t)(warp * 2) * kHeadSmemBytes + kGsDoubles * 8 +
-                                           kLsDoubles * 8);
-    static_assert(kLfFloats >= 256, "table does not fit the L-column buffer");
-#pragma unroll
-    for (int i = lane; i < 256; i += 32) lutw[i] = float(i) / 255.f;
-    __syncwarp();
-    src.lut = lutw;
-  }
   const int rows_live = (P.n_pix + 63) >> 6;
-  float4 xa[4];
+  typename RawQuad<MODE>::type xa[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid && j < rows_live) xa[j] = pix4m<MODE>(src, 64 * j + 4 * l16);
-  }
+  for (int j = 0; j < 4; ++j) xa[j] = pix4raw<MODE>(src, 64 * j + 4 * l16, valid && j < rows_live);
 
   // ---- A_n[(s,l), r] = sum_i U^(n-1)[i][l] U^(n)[2i+s][r]  (D >= 8: bonds 1..3 are the natural 2, 4, 8) ----
   if (valid) {
@@ -620,15 +684,14 @@ gram_head_kernel(const __grid_constant__ EncodeParams P, const double* __restric
       for (int q = 0; q < 4; ++q) acc[l][q] = 0.f;
 #pragma unroll 1
     for (int i0 = 0; i0 < rows_live; i0 += 4) {
-      float4 xb[4];
+      typename RawQuad<MODE>::type xb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        xb[j] = pix4raw<MODE>(src, 64 * (i0 + 4 + j) + 4 * l16, valid && i0 + 4 + j < rows_live);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        xb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && i0 + 4 + j < rows_live) xb[j] = pix4m<MODE>(src, 64 * (i0 + 4 + j) + 4 * l16);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float xv[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
+        const float4 xq = pix4cvt<MODE>(xa[j]);
+        const float xv[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
         for (int l4 = 0; l4 < 4; ++l4) {
           if (4 * l4 >= kept_max) continue;  // warp-uniform: zero columns of U^(3) (13 live rows: rank <= 13)
@@ -678,7 +741,13 @@ inline cudaError_t launch_head(const EncodeParams& P, double* gws, float* ws_psi
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    gram_kernel<MODE><<<grid, kHwWarps * 32, smem_a, st>>>(P, gws);
+    if (MODE == 2 && u8_imma() && (P.ld & 15) == 0 && (P.n_pix & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(P.images) & 15) == 0) {
+      const int64_t want = (P.N + 8 * kGramU8Unroll - 1) / (8 * kGramU8Unroll);
+      gram_u8_kernel<<<(int)std::min<int64_t>(want, 148 * 8), 256, 0, st>>>(P, gws);
+    } else {
+      gram_kernel<MODE><<<grid, kHwWarps * 32, smem_a, st>>>(P, gws);
+    }
     // rows 14 and 15 of X_3 (pixels 896..1023) are padding for MNIST-shaped images: the L columns end there
     if (P.n_pix <= 896) gram_head_kernel<MODE, 7><<<grid, kHwWarps * 32, smem_b, st>>>(P, gws, ws_psi4, keys);
     else gram_head_kernel<MODE, 8><<<grid, kHwWarps * 32, smem_b, st>>>(P, gws, ws_psi4, keys);

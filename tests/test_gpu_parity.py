@@ -223,6 +223,45 @@ def test_empty_and_ragged_batches(gpu_lib):
     assert np.abs(ovu - full).max() < 1e-5 * full.max()
 
 
+@pytest.mark.parametrize("n_pix", [784, 1024])
+def test_uint8_integer_gram_matches_fp64_gram(gpu_lib, n_pix):
+    """uint8 pixels take the exact integer Gram matrix G_3 = X_3 X_3^T from the tensor cores
+    (mma.sync u8 x u8 -> s32) instead of fp64 FMAs over converted pixels: same singular values,
+    states and overlaps as the fp64 route and as the dense fp64 oracle; ragged batch sizes."""
+    from orthogonal_classifiers_b200 import batched
+    base = np.concatenate([synthetic_images(500, seed=41), adversarial_images()])
+    rng = np.random.default_rng(3)
+    if n_pix == 1024:
+        full = rng.random((len(base), 1024))
+        full[:, :784] = np.maximum(full[:, :784] * 0.2, base)
+        base = full
+    u8 = np.rint(base * 255).astype(np.uint8)
+    clf = random_classifier(10, 32, centre=5, seed=6)
+    ref = oracle.overlaps_dense(u8.astype(np.float64) / 255.0, oracle.dense_classifier(clf))
+    for n in (len(u8), 33, 5, 1):
+        new = gpu_lib.encode_images(u8[:n], 32, return_svals=True)
+        ov_new = gpu_lib.label_overlaps(new, clf)
+        batched.set_option("enc_u8mma", 0)
+        try:
+            old = gpu_lib.encode_images(u8[:n], 32, return_svals=True)
+            ov_old = gpu_lib.label_overlaps(old, clf)
+        finally:
+            batched.set_option("enc_u8mma", 1)
+        sn, so = new.svals.cpu().numpy(), old.svals.cpu().numpy()
+        assert np.abs(sn - so).max() <= 2e-6 * so.max()
+        assert np.abs(ov_new - ov_old).max() <= 1e-5 * ov_old.max()
+        assert np.abs(ov_new - ref[:n]).max() <= 1e-5 * ref.max()
+        live = np.abs(u8[:n].astype(np.float64)).sum(1) > 0
+        for i in (0, n // 2, n - 1):
+            if not live[i]:
+                continue
+            a = oracle.mps_to_state([x.astype(np.float64) for x in new.sites_numpy(i)])
+            x = np.zeros(1024)
+            x[:n_pix] = u8[i].astype(np.float64) / 255.0
+            x /= np.linalg.norm(x)
+            assert min(np.abs(a - x).max(), np.abs(a + x).max()) < 1e-5
+
+
 def test_count_correct_and_evaluate(gpu_lib):
     import torch
     rng = np.random.default_rng(5)
