@@ -19,9 +19,9 @@ def timeit(x, reps=10):
     for _ in range(reps): batched.classify_host(x, clf, 32, out=(ov, am))
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
-plans = ["4000,8000,14000,22000,22000", "4000,8000,16000,21000,21000", "5000,9000,14000,21000,21000", "4000,7000,12000,17000,30000",
-         "3000,7000,14000,23000,23000", "4000,8000,14000,20000,24000", "4000,8000,14000,44000", "4000,8000,12000,16000,30000",
-         "2000,4000,8000,14000,21000,21000", "4000,8000,14000,22000,22000", "6000,10000,16000,19000,19000", "4000,8000,14000,14667,14667,14666"]
+plans = ["4000,8000,14000,22000,22000", "3000,6000,12000,24500,24500", "4000,8000,16000,21000,21000", "5000,10000,15000,20000,20000",
+         "4000,8000,12000,16000,30000", "2000,4000,8000,16000,20000,20000", "4000,8000,14000,44000", "6000,12000,26000,26000",
+         "4000,6000,10000,14000,18000,18000", "3000,5000,8000,12000,21000,21000", "4000,8000,14000,22000,22000"]
 for streams in (4, 4):
     batched.set_option("host_streams", streams)
     for p in plans:
