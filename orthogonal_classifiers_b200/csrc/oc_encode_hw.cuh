@@ -1125,9 +1125,10 @@ hw_row4q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict_
 constexpr int kPackOwn = 4 * kSortBins, kPackRec = 5 * kSortBins, kPackMaxRec = 32;
 constexpr int kPackInts = kPackRec + 4 * kPackMaxRec;
 __global__ void hw_pack_prefix_kernel(int32_t* __restrict__ bins, int mix) {
+  __shared__ int rem[kSortBins];  // (a local array indexed at run time lived in local memory: 11 us on one thread)
+  if (threadIdx.x < kSortBins) rem[threadIdx.x] = bins[threadIdx.x];
+  __syncthreads();
   if (threadIdx.x == 0) {
-    int rem[kSortBins];
-    for (int b = 0; b < kSortBins; ++b) rem[b] = bins[b];
     int start = 0, nrec = 0;
     for (int b = kSortBins - 1; b >= 0; --b) {  // longest lines first
       const int c = rem[b];
