@@ -1056,7 +1056,27 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
     if (int rc = hp.am[b].ensure((size_t)chunk * sizeof(int32_t), st)) return rc;
   }
   if ((size_t)clf_elems * esz > hp.clf.cap) hp.clf_bytes = 0;  // a new buffer: the cached upload is gone
-  if (int rc = hp.clf.ensure((size_t)clf_elems * esz, st)) return rc;
+  {
+    const void* old = hp.clf.p;
+    if (int rc = hp.clf.ensure((size_t)clf_elems * esz, st)) return rc;
+    if (old && old != hp.clf.p) {
+      // the old address may be handed to somebody else: no context may keep a re-laid classifier under it
+      for (int i = 0; i < HostPipe::NS; ++i) {
+        if (i > 0 && !hp.comp[i]) continue;
+        Ctx& ci = i == 0 ? cx : get_ctx(hp.comp[i]);
+        std::unique_lock<std::mutex> tmp;
+        if (i >= ns) tmp = std::unique_lock<std::mutex>(ci.mu);
+        for (size_t j = 0; j < ci.cache.size();) {
+          if (ci.cache[j].clf == old) {
+            ci.cache[j].prepared.release(st);
+            ci.cache.erase(ci.cache.begin() + j);
+          } else {
+            ++j;
+          }
+        }
+      }
+    }
+  }
   for (int i = 0; i < ns && i < (int)sizes.size(); ++i)
     if (int rc = hp.mps[i].ensure((size_t)chunk * offs[L] * esz, st)) return rc;
   // The classifier goes up through a pinned staging buffer: a copy from the caller's pageable array is
@@ -1080,11 +1100,25 @@ int oc_classify_host(const void* images_host, int in_dtype, int64_t N, int n_pix
       const unsigned char* t = reinterpret_cast<const unsigned char*>(clf_packed_host);
       for (size_t i = cb & ~(size_t)7; i < cb; ++i) h = (h ^ t[i]) * 1099511628211ull;
     }
-    if (cb != hp.clf_bytes || h != hp.clf_hash || g_host_trace == 2) {
+    const bool changed = cb != hp.clf_bytes || h != hp.clf_hash || g_host_trace == 2;
+    if (changed) {
       memcpy(hp.clf_pin, clf_packed_host, cb);
       OC_CUDA(cudaMemcpyAsync(hp.clf.p, hp.clf_pin, cb, cudaMemcpyHostToDevice, st));
       hp.clf_bytes = cb;
       hp.clf_hash = h;
+    }
+    // the library owns this device copy and knows when it changes: every compute stream's context keeps the
+    // re-laid classifier (the 21 us re-layout kernel ran in front of every chunk's overlap kernel)
+    for (int i = 0; i < ns; ++i) {
+      ClfEntry* ent = nullptr;
+      for (auto& e : cxs_[i]->cache)
+        if (e.clf == hp.clf.p) ent = &e;
+      if (!ent) {
+        cxs_[i]->cache.emplace_back();
+        ent = &cxs_[i]->cache.back();
+        ent->clf = hp.clf.p;
+      }
+      if (changed) ent->key = 0;
     }
   }
   if (two) {  // the library's streams join the caller's stream order: after the classifier upload and everything before the call

@@ -98,6 +98,14 @@ def test_classify_host_c_abi(gpu_lib, in_dtype):
             r_ov, r_am = gpu_lib.classify(imgs[:300], clf, D, trunc=trunc)
             ov, am = gpu_lib.classify_host(imgs[:300], clf, D, trunc=trunc)
             np.testing.assert_array_equal(ov.astype(np.float64), r_ov)
+        # the library keeps its device copy and re-laid form of the classifier while the caller's is unchanged:
+        # another classifier of the same shapes, then the first again (all four compute streams: 5 chunks)
+        batched.set_option("host_chunk", 250)
+        clf_b = gpu_lib.DeviceClassifier(random_classifier(10, 32, centre=5, seed=77))
+        rb_ov, _ = gpu_lib.classify(imgs, clf_b, 32)
+        for c, r in ((clf_b, rb_ov), (clf, ref_ov), (clf_b, rb_ov)):
+            ov, _ = gpu_lib.classify_host(imgs, c, 32)
+            np.testing.assert_array_equal(ov.astype(np.float64), r)
         clf64 = gpu_lib.DeviceClassifier(random_classifier(10, 32, centre=5, seed=2), dtype="f64")
         r_ov, _ = gpu_lib.classify(imgs[:200], clf64, 32, dtype="f64")
         ov, _ = gpu_lib.classify_host(imgs[:200], clf64, 32, dtype="f64")
