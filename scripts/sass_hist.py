@@ -1,5 +1,5 @@
 """SASS opcode histogram of the shipped library, per kernel for the opcodes that prove which units run
-(tensor cores: HMMA = mma.sync, UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st; TMA: UBLKCP = cp.async.bulk;
+(tensor cores: HMMA = mma.sync, IMMA = integer mma.sync, UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st; TMA: UBLKCP = cp.async.bulk;
 packed fp32: FFMA2; fp64: DFMA):  python scripts/sass_hist.py > profiles/sass_r2.txt"""
 import collections, re, subprocess, sys
 lib = sys.argv[1] if len(sys.argv) > 1 else "orthogonal_classifiers_b200/liboc_b200.so"
@@ -26,7 +26,7 @@ for line in out.splitlines():
         op = m.group(1)
         tot[op] += 1
         per[cur][op] += 1
-keys = ["FFMA", "FFMA2", "DFMA", "HMMA", "UTCHMMA", "LDTM", "STTM", "UBLKCP", "SHFL", "LDS", "STS", "LDG", "STG", "MUFU"]
+keys = ["FFMA", "FFMA2", "DFMA", "HMMA", "IMMA", "UTCHMMA", "LDTM", "STTM", "UBLKCP", "SHFL", "LDS", "STS", "LDG", "STG", "MUFU"]
 print("SASS of", lib, "(sm_100a): instructions per kernel, selected opcodes")
 print(f"{'kernel':58s}" + "".join(f"{k:>8s}" for k in keys) + f"{'total':>9s}")
 for name, c in per.items():
