@@ -623,7 +623,7 @@ __device__ __forceinline__ int jacobi_ring(u64 (&T)[NA], u64 (&S)[NA], float& nT
         nS = fS;
       }
     }
-#pragma unroll 1
+#pragma unroll 1  // (unrolled twice the loop loses ~4 % of its instructions and 7 % of its speed: instruction cache)
     for (int rr = 0; rr < mlive_max; ++rr) {
       const bool off = done || rr >= mlive;
       rotate16<0, NE>(T, S, nT, nS, thr2, off, lostf, again);
