@@ -77,6 +77,7 @@ const char* oc_last_error(void);
  *                   idle lanes of a warp also take one image with a shorter line; bit-identical results)
  *   "enc_mgs4" = 0  step 4 without the Gram-Schmidt preconditioning
  *   "enc_qr5"  = 0  step 5 without the pivoted Gram-Schmidt preconditioning
+ *   "enc_qr6"  = 0  step 6 by Jacobi on the 32-element columns instead of Gram-Schmidt + the 8 x 8 factor
  *   "enc_split5" = 0  step 5 as one kernel instead of three
  *   "enc_sort" = 0  no device-side sort of the images by live rows
  *   "enc_split2" = 1  (opt-in) the two halves of an encoder chunk of >= 32,768 images

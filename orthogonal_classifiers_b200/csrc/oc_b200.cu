@@ -611,6 +611,10 @@ int oc_set_option(const char* key, int value) {
     oc::hw::split_step5() = value;
     return OC_OK;
   }
+  if (key && !strcmp(key, "enc_qr6")) {
+    oc::hw::qr_step6() = value;
+    return OC_OK;
+  }
   if (key && !strcmp(key, "enc_qr5")) {
     oc::hw::qr_step5() = value;
     return OC_OK;

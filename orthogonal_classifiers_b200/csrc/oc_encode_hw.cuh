@@ -1375,6 +1375,211 @@ __global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB) hw_col_kernel(const
   }
 }
 
+// ---- step 6, QR-preconditioned like step 5 -----------------------------------------
+// M_6 (32 x 8): column-pivoted Gram-Schmidt in registers -> R (8 x 8, shared memory); one-sided Jacobi on
+// the rows of R (8 vectors of 8 elements instead of 8 columns of 32); the converged vectors sigma_r v_r are
+// the rows of Psi_7; U = M_6 V Sigma^-1 by one product (each lane owns the two vectors it iterated, so the
+// coefficients are already in its registers) and one odd-even sweep of Gram-Schmidt projections.
+// One lane per slot, 4 lanes per image, 8 images per warp, as hw_col_kernel<6>.
+__global__ void __launch_bounds__(kHwWarps * 32, OC_HW_MINB)
+hw_col6q_kernel(const __grid_constant__ EncodeParams P, const float* __restrict__ ws_in, float* __restrict__ ws_out) {
+  constexpr int B = 16, Q = 8, NE = 16, IPW = 8;
+  __shared__ __align__(16) float Rsm[kHwWarps * IPW * Q * Q];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = lane & 3, grp = lane >> 2, gbase = lane & ~3;
+  const int64_t img = ((int64_t)blockIdx.x * kHwWarps + warp) * IPW + grp;
+  const bool valid = img < P.N;
+  const int64_t im = valid ? img : 0;
+  const float* psi = ws_in + (size_t)im * kWsStride;  // Psi_6 [16][16]
+  float* R = Rsm + (size_t)(warp * IPW + grp) * Q * Q;  // R[step][column]
+  // columns (2 slot, 2 slot + 1) of M_6; element e = s * B + l, packed pair j = (e = 2j, 2j + 1)
+  u64 T[16], S[16];
+  {
+    const float* pc = psi + 2 * slot;
+#pragma unroll
+    for (int j = 0; j < NE; ++j) {
+      const int e = 2 * j, sj = e / B, lj = e % B;
+      float2 v0 = make_float2(0.f, 0.f), v1 = v0;
+      if (valid) {
+        v0 = __ldg(reinterpret_cast<const float2*>(pc + lj * 2 * Q + sj * Q));
+        v1 = __ldg(reinterpret_cast<const float2*>(pc + (lj + 1) * 2 * Q + sj * Q));
+      }
+      T[j] = pack2(v0.x, v1.x);
+      S[j] = pack2(v0.y, v1.y);
+    }
+  }
+  float nT = dot16<0, NE>(T, T), nS = dot16<0, NE>(S, S);
+  const float fro = group_sum<2>(nT + nS);
+  const float thr2 = kFloor2 * fro;
+  int nsteps = 0;  // R rows up to the last live pivot
+#pragma unroll 1
+  for (int step = 0; step < Q; ++step) {
+    // pivot: largest remaining (cached, downdated) squared norm; ties -> lowest column
+    unsigned key;
+    {
+      const unsigned kt = nT > 0.f ? ((__float_as_uint(nT) & ~15u) | (unsigned)(15 - 2 * slot)) : 0u;
+      const unsigned ks = nS > 0.f ? ((__float_as_uint(nS) & ~15u) | (unsigned)(14 - 2 * slot)) : 0u;
+      key = kt > ks ? kt : ks;
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {
+        const unsigned other = __shfl_xor_sync(FULL, key, o);
+        key = key > other ? key : other;
+      }
+    }
+    const int pc = 15 - (int)(key & 15u);
+    const int owner = gbase | ((pc >> 1) & 3);
+    u64 qv[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) qv[e] = shfl2((pc & 1) ? S[e] : T[e], owner);
+    float rT = dot16<0, NE>(qv, T), rS = dot16<0, NE>(qv, S);
+    const float qn2 = __shfl_sync(FULL, (pc & 1) ? rS : rT, owner);  // the owner's own dot product is |q|^2
+    const bool dead = key == 0u || !(qn2 > thr2);
+    const float inv2 = dead ? 0.f : 1.f / qn2, invn = dead ? 0.f : rsqrtf(qn2);
+    const bool isT = 2 * slot == pc, isS = 2 * slot + 1 == pc;
+    if (!(nT > 0.f) || isT) rT = 0.f;  // finished columns (norm < 0) and the pivot itself stay
+    if (!(nS > 0.f) || isS) rS = 0.f;
+    const float cT = -rT * inv2, cS = -rS * inv2;
+    const u64 cT2 = pack2(cT, cT), cS2 = pack2(cS, cS);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      T[e] = fma2(cT2, qv[e], T[e]);
+      S[e] = fma2(cS2, qv[e], S[e]);
+    }
+    {
+      const float dg = qn2 * invn;
+      *reinterpret_cast<float2*>(R + step * Q + 2 * slot) = make_float2(isT ? dg : rT * invn, isS ? dg : rS * invn);
+    }
+    nT = isT ? -1.f : (nT > 0.f ? fmaxf(fmaf(cT, rT, nT), 1e-37f) : nT);
+    nS = isS ? -1.f : (nS > 0.f ? fmaxf(fmaf(cS, rS, nS), 1e-37f) : nS);
+    if (!dead) nsteps = step + 1;
+  }
+  __syncwarp();
+  // ---- Jacobi on the rows of R: this lane iterates rows 2 slot, 2 slot + 1 (8 elements each) ----
+#pragma unroll
+  for (int j = 0; j < 16; ++j) T[j] = S[j] = 0ull;
+  {
+    const float* r0 = R + (2 * slot) * Q;
+    const float4 a0 = lds4(r0), a1 = lds4(r0 + 4), b0 = lds4(r0 + Q), b1 = lds4(r0 + Q + 4);
+    T[0] = pack2(a0.x, a0.y); T[1] = pack2(a0.z, a0.w); T[2] = pack2(a1.x, a1.y); T[3] = pack2(a1.z, a1.w);
+    S[0] = pack2(b0.x, b0.y); S[1] = pack2(b0.z, b0.w); S[2] = pack2(b1.x, b1.y); S[3] = pack2(b1.z, b1.w);
+  }
+  const int mlive = (nsteps + 1) >> 1;
+  const int mlive_max = __reduce_max_sync(FULL, mlive);
+  int sweeps = 0;
+  nT = dot16<0, 4>(T, T);
+  nS = dot16<0, 4>(S, S);
+  if (mlive_max > 0) {
+    sweeps = jacobi16<0, 4, 2>(T, S, nT, nS, thr2, lane, mlive, mlive_max);
+    nT = dot16<0, 4>(T, T);
+    nS = dot16<0, 4>(S, S);
+  }
+  int rT, rS;
+  rank16<0, 2>(nT, nS, lane, rT, rS);
+  const Out io = make_out(P, im, 6);
+  const int r_rt = io.r_rt, b_rt = io.b_rt;
+  const bool kT = nT > thr2 && rT < r_rt;
+  const bool kS = nS > thr2 && rS < r_rt;
+  if (valid) {
+    if (io.sv) {
+      if (rT < io.sv_width) io.sv[rT] = nT > thr2 ? sqrtf(nT) : 0.f;
+      if (rS < io.sv_width) io.sv[rS] = nS > thr2 ? sqrtf(nS) : 0.f;
+      for (int k = Q + slot; k < io.sv_width; k += 4) io.sv[k] = 0.f;
+    }
+    if (io.sweeps && slot == 0) *io.sweeps = sweeps;
+    // Psi_7[rank][c] = sigma_r v_r[c]: the converged vector itself
+    float* out = ws_out + (size_t)im * kWsStride;
+    float4 t0, t1, s0, s1;
+    unpack2(T[0], t0.x, t0.y); unpack2(T[1], t0.z, t0.w); unpack2(T[2], t1.x, t1.y); unpack2(T[3], t1.z, t1.w);
+    unpack2(S[0], s0.x, s0.y); unpack2(S[1], s0.z, s0.w); unpack2(S[2], s1.x, s1.y); unpack2(S[3], s1.z, s1.w);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(out + rT * Q) = kT ? t0 : z;
+    *reinterpret_cast<float4*>(out + rT * Q + 4) = kT ? t1 : z;
+    *reinterpret_cast<float4*>(out + rS * Q) = kS ? s0 : z;
+    *reinterpret_cast<float4*>(out + rS * Q + 4) = kS ? s1 : z;
+  }
+  // ---- U = M_6 V Sigma^-1: coefficients (sigma v)[c] / sigma^2 of this lane's two vectors ----
+  u64 cf[Q];  // cf[c] = (coefficient of vector T, of vector S)
+  {
+    const float iT = kT ? 1.f / nT : 0.f, iS = kS ? 1.f / nS : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a0, a1, b0, b1;
+      unpack2(T[e], a0, a1);
+      unpack2(S[e], b0, b1);
+      cf[2 * e] = pack2(a0 * iT, b0 * iS);
+      cf[2 * e + 1] = pack2(a1 * iT, b1 * iS);
+    }
+  }
+  u64 UT[NE], US[NE];
+#pragma unroll
+  for (int j = 0; j < NE; ++j) {
+    u64 acc[2] = {0ull, 0ull};  // (U_T, U_S) of elements e = 2j, 2j + 1
+    const int e = 2 * j, sj = e / B, lj = e % B;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const float* row = psi + (lj + p) * 2 * Q + sj * Q;
+      float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = m0;
+      if (valid) {
+        m0 = ldg4(row);
+        m1 = ldg4(row + 4);
+      }
+      acc[p] = fma2(cf[0], pack2(m0.x, m0.x), acc[p]);
+      acc[p] = fma2(cf[1], pack2(m0.y, m0.y), acc[p]);
+      acc[p] = fma2(cf[2], pack2(m0.z, m0.z), acc[p]);
+      acc[p] = fma2(cf[3], pack2(m0.w, m0.w), acc[p]);
+      acc[p] = fma2(cf[4], pack2(m1.x, m1.x), acc[p]);
+      acc[p] = fma2(cf[5], pack2(m1.y, m1.y), acc[p]);
+      acc[p] = fma2(cf[6], pack2(m1.z, m1.z), acc[p]);
+      acc[p] = fma2(cf[7], pack2(m1.w, m1.w), acc[p]);
+    }
+    float a0, b0, a1, b1;
+    unpack2(acc[0], a0, b0);
+    unpack2(acc[1], a1, b1);
+    UT[j] = pack2(a0, a1);
+    US[j] = pack2(b0, b1);
+  }
+  // ---- polish (one odd-even sweep of projections), normalise, A_6[(s*b + l), rank] ----
+  {
+    float keyT = kT ? nT : 0.f, keyS = kS ? nS : 0.f;
+    int tagT = rT, tagS = rS;
+    polish_ring<NE>(UT, US, keyT, keyS, tagT, tagS, lane, 4, gbase, mlive, mlive_max);
+    const bool tiny = (keyT > 0.f && keyT < 1e3f * thr2) || (keyS > 0.f && keyS < 1e3f * thr2);  // as in step 5
+    if (__any_sync(FULL, tiny)) {
+      polish_ring<NE>(UT, US, keyT, keyS, tagT, tagS, lane, 4, gbase, mlive, mlive_max);
+      polish_ring<NE>(UT, US, keyT, keyS, tagT, tagS, lane, 4, gbase, mlive, mlive_max);
+    }
+    u64 qT = 0ull, qS = 0ull;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      qT = fma2(UT[e], UT[e], qT);
+      qS = fma2(US[e], US[e], qS);
+    }
+    const float jT = keyT > 0.f ? rsqrtf(hsum2(qT)) : 0.f;
+    const float jS = keyS > 0.f ? rsqrtf(hsum2(qS)) : 0.f;
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < NE; ++j) {
+        float t0, t1, s0, s1;
+        unpack2(UT[j], t0, t1);
+        unpack2(US[j], s0, s1);
+        const int e = 2 * j, sj = e / B, la = e % B, lb = la + 1;
+        if (la < b_rt) {
+          if (tagT < r_rt) io.A[(sj * b_rt + la) * r_rt + tagT] = t0 * jT;
+          if (tagS < r_rt) io.A[(sj * b_rt + la) * r_rt + tagS] = s0 * jS;
+        }
+        if (lb < b_rt) {
+          if (tagT < r_rt) io.A[(sj * b_rt + lb) * r_rt + tagT] = t1 * jT;
+          if (tagS < r_rt) io.A[(sj * b_rt + lb) * r_rt + tagS] = s1 * jS;
+        }
+      }
+    }
+  }
+}
+inline int& qr_step6() {
+  static int v = 1;
+  return v;
+}
+
 // ---- step 5, QR-preconditioned ---------------------------------------------------
 // M_5 (64 x 16, columns spread over the two lanes of a slot) = Q R by one pass of
 // column-pivoted modified Gram-Schmidt in registers; the right singular vectors and
@@ -1953,7 +2158,8 @@ inline cudaError_t launch_chain(const EncodeParams& P, float* ws0, float* ws1, v
   ee.mark(4, st);
   // tail: steps 6 and 7 with 8 / 16 images per warp, steps 8-9 one thread per image
   const int ipc6 = kHwWarps * ColShape<6>::IPW, ipc7 = kHwWarps * ColShape<7>::IPW;
-  hw_col_kernel<6><<<(int)((P.N + ipc6 - 1) / ipc6), kHwWarps * 32, 0, st>>>(P, ws1, ws0);
+  if (qr_step6()) hw_col6q_kernel<<<(int)((P.N + ipc6 - 1) / ipc6), kHwWarps * 32, 0, st>>>(P, ws1, ws0);
+  else hw_col_kernel<6><<<(int)((P.N + ipc6 - 1) / ipc6), kHwWarps * 32, 0, st>>>(P, ws1, ws0);
   hw_col_kernel<7><<<(int)((P.N + ipc7 - 1) / ipc7), kHwWarps * 32, 0, st>>>(P, ws0, ws1);
   hw_tail89_kernel<<<(int)((P.N + 127) / 128), 128, 0, st>>>(P, ws1);
   ee.mark(5, st);

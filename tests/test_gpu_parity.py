@@ -342,7 +342,7 @@ def test_generic_and_specialised_kernels_agree(gpu_lib):
             assert np.abs(ov_fast - ov_gen).max() <= 1e-5 * ov_gen.max()
 
 
-@pytest.mark.parametrize("option", ["enc_gram", "enc_pack", "enc_mgs4", "enc_qr5", "enc_split5", "ov_static", "ov_mma", "ov_pad"])
+@pytest.mark.parametrize("option", ["enc_gram", "enc_pack", "enc_mgs4", "enc_qr5", "enc_qr6", "enc_split5", "ov_static", "ov_mma", "ov_pad"])
 def test_alternative_code_paths_agree(gpu_lib, option):
     """Every fast path has its predecessor behind an option: the Gram-matrix front
     end (steps 0-3) vs. the Jacobi head kernels, the packed step 4 vs. the paired
