@@ -626,11 +626,17 @@ __device__ __forceinline__ int jacobi_ring(u64 (&T)[NA], u64 (&S)[NA], float& nT
 #pragma unroll 1  // (unrolled twice the loop loses ~4 % of its instructions and 7 % of its speed: instruction cache)
     for (int rr = 0; rr < mlive_max; ++rr) {
       const bool off = done || rr >= mlive;
-      rotate16<0, NE>(T, S, nT, nS, thr2, off, lostf, again);
+#ifndef OC_RING_QP
+#define OC_RING_QP(ne) ((ne) == 16)
+#endif
+      // which round forms its products on which operand (rotate16<KEEPA>) decides how many register moves
+      // ptxas leaves at the end of the round pair; the better assignment differs between instantiations
+      // (26-element loop: 21 moves with (false, true), 32-element loop: 71 with that and 19 with (true, false))
+      rotate16<0, NE, OC_RING_QP(NE)>(T, S, nT, nS, thr2, off, lostf, again);
 #pragma unroll
       for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_dn);
       float nR = __shfl_sync(FULL, nT, src_dn);
-      rotate16<0, NE, true>(S, T, nS, nR, thr2, off || idleB, lostf, again);
+      rotate16<0, NE, !OC_RING_QP(NE)>(S, T, nS, nR, thr2, off || idleB, lostf, again);
 #pragma unroll
       for (int e = 0; e < NE; ++e) T[e] = shfl2(T[e], src_up);
       nT = __shfl_sync(FULL, nR, src_up);
