@@ -17,7 +17,7 @@ python scripts/u8_gram_time.py > gpurun_out/u8_gram_time_r2f.log 2>&1
 ;;
 2)
 python scripts/one_step.py > /dev/null 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -s 17 -c 17 -o gpurun_out/step_r2f -f python scripts/one_step.py > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -s 16 -c 16 -o gpurun_out/step_r2f -f python scripts/one_step.py > gpurun_out/ncu2.log 2>&1
 ls -la gpurun_out/step_r2f.ncu-rep
 ;;
 3)
