@@ -1144,7 +1144,9 @@ __global__ void hw_pack_prefix_kernel(int32_t* __restrict__ bins, int mix) {
       bins[kSortBins + b] = start;
       bins[2 * kSortBins + b] = 0;
       bins[kPackOwn + b] = c;
-      if (mix && ipw < 4) {
+      // (no guests in the 32-element instantiation, b > kQ4NE: its rotations round differently - see OC_RING_QP -
+      // and an image's bits must not depend on its warp)
+      if (mix && ipw < 4 && b <= kQ4NE) {
         int filled = 0;
         const int freel = 32 - ipw * gs;
         for (int g = freel < b - 1 ? freel : b - 1; g >= 2 && filled < W && nrec < kPackMaxRec; --g) {

@@ -496,6 +496,37 @@ def test_encoding_does_not_depend_on_batch_composition(gpu_lib):
     assert torch_equal(mixed.data, plain.data) and torch_equal(mixed.svals, plain.svals)
 
 
+def test_packed_step4_guest_plans(gpu_lib):
+    """The guest plan of the packed step 4 for line lengths the stroke images do not produce: images with
+    exactly k non-zero 64-pixel rows, k = 1..16, in lopsided proportions (more guests than hosts, hosts
+    without guests, 14- to 16-lane hosts whose free lanes only fit 2- to 4-lane guests, an empty image).
+    Same bits with and without guests; amplitudes against the normalised image."""
+    from orthogonal_classifiers_b200 import batched
+    rng = np.random.default_rng(17)
+    counts = {1: 7, 2: 40, 3: 9, 4: 33, 5: 5, 6: 61, 7: 3, 8: 90, 9: 11, 10: 150, 11: 64, 12: 37, 13: 201, 14: 23, 15: 18, 16: 12}
+    imgs = [np.zeros(1024)]
+    for k, n in counts.items():
+        for _ in range(n):
+            x = np.zeros((16, 64))
+            x[:k] = rng.random((k, 64)) * (rng.random((k, 1)) + 0.05)
+            imgs.append(x.reshape(-1))
+    imgs = np.stack(imgs)[rng.permutation(len(imgs))].astype(np.float32)
+    mixed = gpu_lib.encode_images(imgs, 32, return_svals=True)
+    batched.set_option("enc_mix", 0)
+    try:
+        plain = gpu_lib.encode_images(imgs, 32, return_svals=True)
+    finally:
+        batched.set_option("enc_mix", 1)
+    assert torch_equal(mixed.data, plain.data) and torch_equal(mixed.svals, plain.svals)
+    for i in range(0, len(imgs), 37):
+        x = imgs[i].astype(np.float64)
+        if not x.any():
+            continue
+        x /= np.linalg.norm(x)
+        a = oracle.mps_to_state([t.astype(np.float64) for t in mixed.sites_numpy(i)])
+        assert min(np.abs(a - x).max(), np.abs(a + x).max()) < 1e-5, i
+
+
 def test_scale_invariance_and_low_contrast(gpu_lib):
     """The MPS is unit norm (the final 1x1 S.V is dropped), so the overlaps must
     not depend on the pixel scale: every threshold in the encoder is relative.
