@@ -189,6 +189,27 @@ def test_overlap_kernel_matches_chain_oracle(gpu_lib, dtype, D_enc, D_clf, centr
     assert np.abs(ov - ref).max() <= TOL[dtype] * ref.max()
 
 
+@pytest.mark.parametrize("n_pix", [520, 832, 840, 896, 900, 1000])
+def test_pixel_counts_around_the_kernel_thresholds(gpu_lib, n_pix):
+    """L = 10 images whose pixel count sits on either side of the encoder's structural shortcuts (rows 13-15 of
+    X_3 empty: n_pix <= 832 / 896), float32 and uint8 pixels (16-byte aligned rows take the integer Gram kernel,
+    the others the fp64 one): amplitudes against the normalised image."""
+    rng = np.random.default_rng(n_pix)
+    u8 = (rng.random((40, n_pix)) * 255 * (rng.random((40, n_pix)) < 0.6)).astype(np.uint8)
+    u8[0] = 0
+    for imgs in (u8, (u8.astype(np.float32) / 255.0)):
+        batch = gpu_lib.encode_images(imgs, 32)
+        assert batch.L == 10
+        for i in range(40):
+            x = np.zeros(1024)
+            x[:n_pix] = u8[i].astype(np.float64) / 255.0
+            st = oracle.mps_to_state([t.astype(np.float64) for t in batch.sites_numpy(i)])
+            if not x.any():
+                assert not st.any()
+                continue
+            assert _state_err(st, x / np.linalg.norm(x)) < 1e-5, (n_pix, imgs.dtype, i)
+
+
 def test_small_chains_and_untruncated_vectors(gpu_lib):
     """mps_encoding(label_vectors_16, None) (experiments.py:679,689): L = 4."""
     rng = np.random.default_rng(0)
