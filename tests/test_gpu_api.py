@@ -120,6 +120,28 @@ def test_classify_host_c_abi(gpu_lib, in_dtype):
                                      clf.packed_host.size, clf._bonds_c, clf._s_c, ref_ov.ctypes.data, None, None) == 1
 
 
+def test_classify_host_default_schedule(gpu_lib):
+    """The default schedule of oc_classify_host on a batch large enough for it - four compute streams, the
+    ramp 4,000 / 8,000 / 14,000 / 22,000 for uint8 pixels, eight staging buffers reused (> 8 chunks of float32) -
+    returns exactly what one device-resident call returns, for every stream count."""
+    from orthogonal_classifiers_b200 import batched
+    base = np.concatenate([synthetic_images(3000, seed=5), adversarial_images()])
+    reps = 85000 // len(base) + 1
+    f32 = np.tile(base, (reps, 1))[:85000].astype(np.float32)
+    u8 = np.rint(f32 * 255).astype(np.uint8)
+    clf = gpu_lib.DeviceClassifier(random_classifier(10, 32, centre=5, seed=9))
+    for imgs in (u8, f32):
+        ref_ov, ref_am = gpu_lib.classify(imgs, clf, 32)
+        try:
+            for streams in (4, 2, 1):
+                batched.set_option("host_streams", streams)
+                ov, am = gpu_lib.classify_host(imgs, clf, 32)
+                np.testing.assert_array_equal(ov.astype(np.float64), ref_ov)
+                np.testing.assert_array_equal(am, ref_am)
+        finally:
+            batched.set_option("host_streams", 4)
+
+
 def test_classifier_files_round_trip(gpu_lib, golden, tmp_path):
     """tools.py:262-291: save one ``site_{i}.npy`` per site, load them back (squeezed
     dimensions re-expanded), classify with the loaded classifier."""
